@@ -1,0 +1,210 @@
+// zk_api.cu -- the batch half of the C ABI (include/zeekstd_b200.h): context + zk_{de,}compress_frames[_dev].
+// The API-mirror half (SeekTable / RawEncoder / Encoder / Decoder) lives in zk_host.cpp and is built on
+// top of these entry points only.
+#include "zk_ctx.h"
+#include "../../include/zeekstd_b200.h"
+#include <stdlib.h>
+#include <vector>
+
+#ifndef ZK_EMUL
+#define ZK_RT_OK(x) do { if ((x) != cudaSuccess) { (void)cudaGetLastError(); return ZK_ERR_NO_DEVICE; } } while (0)
+#else
+#define ZK_RT_OK(x) do { (void)(x); } while (0)
+#endif
+
+static size_t zk_env_size(const char* name, size_t dflt) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return (size_t)strtoull(s, nullptr, 10);
+}
+
+extern "C" const char* zk_version(void) {
+#ifdef ZK_EMUL
+    return "zeekstd_b200 0.1 (ZK_EMUL test build: device code interpreted on the CPU; not a product build)";
+#else
+    return "zeekstd_b200 0.1 (sm_100a)";
+#endif
+}
+
+extern "C" const char* zk_error_name(int32_t rc) {
+    switch (rc) {
+    case 0: return "No error detected";
+    case ZK_ERR_NUMBER_CONVERSION: return "number conversion failed";
+    case ZK_ERR_OFFSET_OUT_OF_RANGE: return "offset out of range";
+    case ZK_ERR_FRAME_INDEX_TOO_LARGE: return "frame index too large";
+    case ZK_ERR_IO: return "io error";
+    case ZK_ERR_NO_DEVICE: return "no usable CUDA device (zeekstd_b200 has no CPU fallback)";
+    case ZK_ERR_INVALID_ARG: return "invalid argument";
+    // strings of ZSTD_getErrorName for the codes this codec can raise
+    case -1: return "Error (generic)";
+    case -10: return "Unknown frame descriptor";
+    case -12: return "Version not supported";
+    case -14: return "Unsupported frame parameter";
+    case -16: return "Frame requires too much memory for decoding";
+    case -20: return "Data corruption detected";
+    case -22: return "Restored data doesn't match checksum";
+    case -32: return "Dictionary mismatch";
+    case -42: return "Parameter is out of bound";
+    case -64: return "Allocation error : not enough memory";
+    case -70: return "Destination buffer is too small";
+    case -72: return "Src size is incorrect";
+    default: return "Unspecified error code";
+    }
+}
+
+int zk_slot_ensure(ZkSlot* s, size_t need_in, size_t need_out) {
+    if (s->cap_in < need_in) {
+        if (s->d_in) cudaFree(s->d_in);
+        s->d_in = nullptr; s->cap_in = 0;
+        size_t want = need_in + need_in / 8 + 256;
+        if (cudaMalloc((void**)&s->d_in, want) != cudaSuccess) return ZK_ERR_ZSTD(ZKZ_MEMORY_ALLOCATION);
+        s->cap_in = want;
+    }
+    if (s->cap_out < need_out) {
+        if (s->d_out) cudaFree(s->d_out);
+        s->d_out = nullptr; s->cap_out = 0;
+        size_t want = need_out + need_out / 8 + 256;
+        if (cudaMalloc((void**)&s->d_out, want) != cudaSuccess) return ZK_ERR_ZSTD(ZKZ_MEMORY_ALLOCATION);
+        s->cap_out = want;
+    }
+    return 0;
+}
+
+extern "C" int32_t zk_ctx_create(int32_t device_ordinal, uint32_t flags, zk_ctx** out) {
+    (void)flags;
+    if (!out) return ZK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { (void)cudaGetLastError(); return ZK_ERR_NO_DEVICE; }
+    if (device_ordinal < 0 || device_ordinal >= ndev) return ZK_ERR_INVALID_ARG;
+    ZK_RT_OK(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    ZK_RT_OK(cudaGetDeviceProperties(&prop, device_ordinal));
+    zk_ctx* c = new zk_ctx();
+    c->device = device_ordinal;
+    c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    for (int i = 0; i < ZK_SLOTS; i++) {
+        if (cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZK_ERR_NO_DEVICE; }
+        c->slot[i].dws.sm_count = c->sm_count;
+        c->slot[i].ews.sm_count = c->sm_count;
+    }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    *out = c;
+    return 0;
+}
+
+extern "C" void zk_ctx_destroy(zk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < ZK_SLOTS; i++) {
+        ZkSlot& s = c->slot[i];
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        zk_decode_ws_free(&s.dws);
+        zk_encode_ws_free(&s.ews);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+extern "C" uint64_t zk_ctx_kernel_launches(const zk_ctx* c) { return c ? c->launches() : 0; }
+extern "C" float zk_ctx_last_device_ms(const zk_ctx* c) { return c ? c->last_ms : 0.f; }
+extern "C" size_t zk_compress_bound(size_t n, uint32_t frame_size) { return zk_encode_bound(n, frame_size); }
+
+// ---------------------------------------------------------------------------------------------
+// decompress
+// ---------------------------------------------------------------------------------------------
+// split [0,n) into sub-batches bounded by output bytes so scratch stays proportional to the sub-batch
+static uint32_t zk_next_sub(const uint64_t* d_off, uint32_t first, uint32_t n, size_t max_bytes, uint32_t max_entries) {
+    uint32_t e = first + 1;
+    while (e < n && e - first < max_entries && d_off[e + 1] - d_off[first] <= max_bytes) e++;
+    return e;
+}
+
+extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const uint64_t* c_off, const uint64_t* d_off,
+                                            uint32_t n, void* d_dst, int32_t verify, int32_t* status, void* cuda_stream) {
+    if (!c || (n && (!d_comp || !c_off || !d_off || !d_dst))) return ZK_ERR_INVALID_ARG;
+    if (n == 0) return 0;
+    ZK_RT_OK(cudaSetDevice(c->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->slot[0].stream;
+    const size_t sub_bytes = zk_env_size("ZK_DEV_SUB_BYTES", (size_t)1 << 30);
+    ZkDecodeWs* ws = &c->slot[0].dws;
+    cudaEventRecord(c->ev0, st);
+    int32_t worst = 0;
+    for (uint32_t first = 0; first < n;) {
+        uint32_t end = zk_next_sub(d_off, first, n, sub_bytes, 1u << 20);
+        int rc = zk_decode_batch(ws, st, (const uint8_t*)d_comp, c_off + first, d_off + first, end - first, (uint8_t*)d_dst,
+                                 verify, status ? status + first : nullptr, (int)zk_env_size("ZK_EXEC_WARPS", 0));
+        if (rc && !worst) worst = rc;
+        if (rc == -(int)ZKZ_GENERIC || rc == -(int)ZKZ_MEMORY_ALLOCATION) return rc;
+        first = end;
+    }
+    cudaEventRecord(c->ev1, st);
+    cudaEventSynchronize(c->ev1);
+    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    return worst;
+}
+
+struct ZkSubDec { uint32_t first = 0, count = 0; std::vector<uint64_t> c_rel, d_rel; bool busy = false; };
+
+static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
+                              uint8_t* dst, int verify) {
+    ZkSlot& s = c->slot[si];
+    uint32_t f = sb.first, cnt = sb.count;
+    size_t cbytes = (size_t)(c_off[f + cnt] - c_off[f]), obytes = (size_t)(d_off[f + cnt] - d_off[f]);
+    int rc = zk_slot_ensure(&s, cbytes + 32, obytes + 32);
+    if (rc) return rc;
+    sb.c_rel.resize(cnt + 1); sb.d_rel.resize(cnt + 1);
+    for (uint32_t j = 0; j <= cnt; j++) { sb.c_rel[j] = c_off[f + j] - c_off[f]; sb.d_rel[j] = d_off[f + j] - d_off[f]; }
+    ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
+    rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
+                           (int)zk_env_size("ZK_EXEC_WARPS", 0));
+    if (rc) return rc;
+    if (obytes) ZK_RT_OK(cudaMemcpyAsync(dst + d_off[f], s.d_out, obytes, cudaMemcpyDeviceToHost, s.stream));
+    sb.busy = true;
+    return 0;
+}
+
+static int zk_dec_sub_finish(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
+                             uint8_t* dst, int verify, int32_t* status) {
+    ZkSlot& s = c->slot[si];
+    if (!sb.busy) return 0;
+    int rc = zk_decode_collect(&s.dws, s.stream, status ? status + sb.first : nullptr);
+    if (rc == ZK_ST_RETRY) {            // scratch was too small for this sub-batch: exact needs are known now
+        rc = zk_dec_sub_enqueue(c, si, sb, comp, c_off, d_off, dst, verify);
+        if (rc) { sb.busy = false; return rc; }
+        rc = zk_decode_collect(&s.dws, s.stream, status ? status + sb.first : nullptr);
+        if (rc == ZK_ST_RETRY) rc = ZK_ERR_ZSTD(ZKZ_MEMORY_ALLOCATION);
+    }
+    sb.busy = false;
+    return rc;
+}
+
+extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
+                                        uint32_t n, uint8_t* dst, int32_t verify, int32_t* status) {
+    if (!c || (n && (!comp || !c_off || !d_off || !dst))) return ZK_ERR_INVALID_ARG;
+    if (n == 0) return 0;
+    ZK_RT_OK(cudaSetDevice(c->device));
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);
+    ZkSubDec sub[ZK_SLOTS];
+    int32_t worst = 0;
+    uint32_t k = 0;
+    for (uint32_t first = 0; first < n; k++) {
+        int si = (int)(k % ZK_SLOTS);
+        int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
+        if (rc && !worst) worst = rc;
+        uint32_t end = zk_next_sub(d_off, first, n, sub_bytes, 1u << 20);
+        sub[si].first = first; sub[si].count = end - first;
+        rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify);
+        if (rc) { if (!worst) worst = rc; break; }
+        first = end;
+    }
+    for (int si = 0; si < ZK_SLOTS; si++) {
+        int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
+        if (rc && !worst) worst = rc;
+    }
+    return worst;
+}

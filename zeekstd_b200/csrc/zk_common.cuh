@@ -1,0 +1,228 @@
+// zk_common.cuh -- shared device/host definitions for the zeekstd_b200 codec kernels.
+//
+// The codec arithmetic that the reference reaches through zstd-safe -> libzstd
+// (lib/src/encode.rs:341-345,444-448; lib/src/decode.rs:243-245) is implemented here from the
+// Zstandard format (RFC 8878; restated in SURVEY.md Appendix A) as CUDA for sm_100a.
+#pragma once
+
+#ifdef ZK_EMUL
+// tests/emul/cuda_emul.h is force-included by the emulation test build (g++), see tests/emul/.
+#define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define ZK_DYN_SMEM(name) uint8_t* name = emu::g_dyn_smem
+#define ZK_SPIN() emu::yield()
+#else
+#include <cuda_runtime.h>
+#define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define ZK_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#define ZK_SPIN() __nanosleep(20)
+#endif
+
+#include <stdint.h>
+#include <stddef.h>
+
+// libzstd's numeric error codes (ZSTD_ErrorCode); the C ABI reports -(code) so that the
+// reference's Error::is_zstd()/get_error_name() semantics carry over (error.rs:40-45, 101-113).
+enum ZkZstdCode : int {
+    ZKZ_OK = 0,
+    ZKZ_GENERIC = 1,
+    ZKZ_PREFIX_UNKNOWN = 10,
+    ZKZ_VERSION_UNSUPPORTED = 12,
+    ZKZ_FRAMEPARAM_UNSUPPORTED = 14,
+    ZKZ_WINDOW_TOO_LARGE = 16,
+    ZKZ_CORRUPTION = 20,
+    ZKZ_CHECKSUM_WRONG = 22,
+    ZKZ_DICT_WRONG = 32,
+    ZKZ_PARAM_OUT_OF_BOUND = 42,
+    ZKZ_MEMORY_ALLOCATION = 64,
+    ZKZ_DST_TOO_SMALL = 70,
+    ZKZ_SRC_SIZE_WRONG = 72,
+};
+
+#define ZK_BLOCK_MAX (1u << 17)          // Block_Maximum_Size, A.2
+#define ZK_MAGIC 0xFD2FB528u
+#define ZK_SKIPPABLE_MASK 0xFFFFFFF0u
+#define ZK_SKIPPABLE_MAGIC 0x184D2A50u
+
+// -------------------------------------------------------------------------------------------
+// Work descriptors living in HBM scratch (one batch = up to 2^31 output bytes).
+// -------------------------------------------------------------------------------------------
+struct ZkBlock {                 // one zstd block of one seek-table entry
+    uint32_t src;                // offset of the block content, relative to the entry's first compressed byte
+    uint32_t size;               // Block_Size (content bytes; for RLE the regenerated size)
+    uint32_t entry;              // seek-table entry this block belongs to
+    uint8_t type;                // 0 Raw, 1 RLE, 2 Compressed
+    uint8_t flags;               // ZKB_*
+    uint8_t lit_kind;            // (entropy kernel) 0 raw-in-place, 1 rle, 2 scratch
+    uint8_t lit_byte;            // rle literal byte
+    uint32_t lit_base;           // literal scratch offset (bytes)            [scan kernel]
+    uint32_t seq_base;           // sequence scratch offset (entries)         [scan kernel]
+    uint32_t nseq;               //                                             [scan kernel]
+    uint32_t lit_size;           // regenerated literal bytes                  [scan kernel]
+    uint32_t lit_src;            // raw literals: offset rel. to entry start   [entropy kernel]
+    uint32_t regen;              // regenerated block size                     [entropy kernel]
+    int32_t status;              // 0 or -(zstd code)                          [entropy kernel]
+    int32_t huf_ref;             // block index whose Huffman tree a Treeless block reuses (-1 none)
+    int32_t ll_ref, of_ref, ml_ref;   // block index defining the table a Repeat mode reuses (-1 none)
+    uint32_t rep_out[3];         // rep-offset state after this block: concrete value, or ZK_SYM|slot<<28|delta
+    uint64_t fcs;                // last block of a zstd frame: Frame_Content_Size if ZKB_HAS_FCS
+    uint32_t hash_start;         // last block: start (rel. to entry output) and length of the zstd frame's content
+    uint32_t hash_len;
+};
+#define ZKB_FIRST 1u             // first block of a zstd frame: resets repeat offsets / entropy tables
+#define ZKB_LAST 2u              // Last_Block
+#define ZKB_HAS_CSUM 4u          // 4-byte content checksum follows the last block
+#define ZKB_HAS_FCS 8u
+
+// symbolic repeat offset: "incoming repeat slot s (0..2) minus delta" (delta in 0..2^20)
+#define ZK_SYM 0x80000000u
+#define ZK_SYM_MAKE(slot, delta) (ZK_SYM | ((uint32_t)(slot) << 28) | (uint32_t)(delta))
+#define ZK_SYM_SLOT(v) (((v) >> 28) & 3u)
+#define ZK_SYM_DELTA(v) ((v) & 0x0FFFFFFFu)
+
+struct ZkEntry {                 // one seek-table entry (one "frame" of the seekable format)
+    uint32_t first_block;
+    uint32_t n_blocks;
+    int32_t status;              // 0, -(zstd code), or ZK_ST_RETRY
+    uint32_t produced;           // bytes written (exec kernel)
+};
+#define ZK_ST_RETRY 0x7FFFFFFF   // scratch capacity exceeded: host grows the workspace and re-runs
+
+struct ZkCounters {
+    unsigned long long n_blocks, n_lit, n_seq;   // exact needs (accumulated even when over capacity)
+    uint32_t overflow;
+    uint32_t n_errors;
+};
+
+// -------------------------------------------------------------------------------------------
+// helpers
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t zk_ld_u8(const uint8_t* p) { return *p; }
+__device__ __forceinline__ uint32_t zk_ld_le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t zk_ld_le24(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+__device__ __forceinline__ uint32_t zk_ld_le32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ int zk_highbit(uint32_t v) { return 31 - __clz((int)v); }   // v != 0
+
+// -------------------------------------------------------------------------------------------
+// Backward bitstream reader (A.7) over global memory with a 128-bit register window.
+//
+// Coordinates: bit i of the stream lives at absolute bit (i + shift) of the 8-byte aligned word
+// array starting at a0 = stream address rounded down to 8.  The window holds the two aligned
+// 64-bit words [wbase/64, wbase/64+1]; one more word is prefetched so a refill never waits
+// on memory.  Reads below the start of the stream return zero bits (legal only at the very
+// end of Huffman-weight / Huffman-literal streams, A.4) and make `bp` negative, which callers
+// test for to detect corruption.
+// -------------------------------------------------------------------------------------------
+struct ZkBackBits {
+    const unsigned long long* a0;   // aligned base
+    unsigned long long hi, lo, nxt; // window words: hi = word(k+1), lo = word(k), nxt = word(k-1)
+    int k;                          // index of `lo`
+    int shift;                      // stream bit 0 = absolute bit `shift`
+    int bp;                         // cursor: number of unread stream bits (may go negative)
+    unsigned long long lowmask;     // mask clearing the bits below the stream start in word 0
+
+    __device__ __forceinline__ unsigned long long word(int idx) const {
+        if (idx < 0) return 0ull;
+        unsigned long long w = a0[idx];
+        return idx == 0 ? (w & lowmask) : w;
+    }
+    // returns false when the stream is malformed (empty or no end marker)
+    __device__ __forceinline__ bool init(const uint8_t* p, uint32_t n) {
+        if (n == 0) return false;
+        uint32_t last = p[n - 1];
+        if (last == 0) return false;
+        uintptr_t addr = (uintptr_t)p;
+        a0 = (const unsigned long long*)(addr & ~(uintptr_t)7);
+        shift = (int)(addr & 7) * 8;
+        lowmask = ~0ull << shift;
+        bp = (int)(n - 1) * 8 + zk_highbit(last);
+        // window must contain [cursor-64, cursor): place hi = word containing absolute bit (bp+shift-1)... or above
+        int top = (bp + shift + 63) >> 6;       // number of words needed to cover the cursor
+        k = top - 2;
+        hi = word(k + 1); lo = word(k); nxt = word(k - 1);
+        return true;
+    }
+    // make sure at least 64 bits below the cursor are inside the window
+    __device__ __forceinline__ void refill() {
+        int rel = bp + shift - k * 64;          // cursor position inside the window, (0,128]
+        if (rel < 64) { hi = lo; lo = nxt; k--; nxt = word(k - 1); }
+    }
+    // n in [0,32]; the n bits just below the cursor, cursor unchanged.  Requires refill() since the last 64 consumed bits.
+    __device__ __forceinline__ uint32_t peek(int n) const {
+        int o = bp + shift - k * 64 - n;         // bit offset of the field inside the window, >= 32 after refill()
+        unsigned long long v;
+        if (o >= 64) v = hi >> (o - 64);
+        else v = (lo >> o) | ((hi << 1) << (63 - o));
+        return (uint32_t)v & (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
+    }
+    __device__ __forceinline__ uint32_t read(int n) { uint32_t v = peek(n); bp -= n; return v; }
+};
+
+// Forward little-endian bit reader for FSE table descriptions (A.6); byte-wise, bounds checked.
+struct ZkFwdBits {
+    const uint8_t* p; uint32_t n; uint32_t bit;
+    __device__ __forceinline__ uint32_t peek(int nb) const {
+        uint32_t byte = bit >> 3, sh = bit & 7;
+        unsigned long long v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { uint32_t b = byte + i < n ? p[byte + i] : 0u; v |= (unsigned long long)b << (8 * i); }
+        return (uint32_t)(v >> sh) & ((1u << nb) - 1u);
+    }
+};
+
+// -------------------------------------------------------------------------------------------
+// FSE decoding tables (A.6).  Sequence tables use the "fat" cell libzstd also uses so that one
+// shared-memory load yields everything a symbol needs.
+// -------------------------------------------------------------------------------------------
+struct __align__(8) ZkSeqCell {
+    uint32_t base_value;     // LL/ML: length baseline; OF: 1 << code
+    uint16_t next_base;      // next-state baseline
+    uint8_t add_bits;        // extra bits to read for the value
+    uint8_t nb_bits;         // bits to read for the next state
+};
+
+__constant__ uint32_t ZK_LL_BASE[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536};
+__constant__ uint8_t ZK_LL_BITS[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16};
+__constant__ uint32_t ZK_ML_BASE[53] = {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539};
+__constant__ uint8_t ZK_ML_BITS[53] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16};
+__constant__ int16_t ZK_LL_DEFAULT[36] = {4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1};
+__constant__ int16_t ZK_ML_DEFAULT[53] = {1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1};
+__constant__ int16_t ZK_OF_DEFAULT[29] = {1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1};
+
+// Parse an FSE normalized-count header.  Returns bytes consumed (>0) or 0 on corruption.
+// counts[] gets nsym entries (-1 = "less than one").
+__device__ inline uint32_t zk_fse_read_ncount(const uint8_t* p, uint32_t n, int max_log, int max_sym,
+                                              int16_t* counts, int* nsym_out, int* log_out) {
+    if (n < 1) return 0;
+    ZkFwdBits f = { p, n, 0 };
+    int al = 5 + (int)f.peek(4); f.bit += 4;
+    if (al > max_log) return 0;
+    int remaining = (1 << al) + 1, threshold = 1 << al, nb = al + 1, s = 0;
+    while (remaining > 1 && s <= max_sym) {
+        int mx = 2 * threshold - 1 - remaining, v;
+        int lo = (int)f.peek(nb - 1);
+        if (lo < mx) { v = lo; f.bit += nb - 1; }
+        else { v = (int)f.peek(nb); if (v >= threshold) v -= mx; f.bit += nb; }
+        int c = v - 1;
+        remaining -= c < 0 ? -c : c;
+        counts[s++] = (int16_t)c;
+        if (c == 0) {
+            for (;;) {
+                int r = (int)f.peek(2); f.bit += 2;
+                for (int q = 0; q < r && s <= max_sym; q++) counts[s++] = 0;
+                if (r != 3) break;
+                if ((f.bit >> 3) > n) return 0;
+            }
+        }
+        if (remaining < 1) return 0;
+        while (remaining < threshold) { nb--; threshold >>= 1; }
+        if ((f.bit >> 3) > n) return 0;
+    }
+    if (remaining != 1 || s > max_sym + 1) return 0;
+    uint32_t used = (f.bit + 7) >> 3;
+    if (used > n) return 0;
+    *nsym_out = s; *log_out = al;
+    return used;
+}

@@ -1,0 +1,30 @@
+// zk_ctx.h -- the context behind the C ABI's opaque zk_ctx (include/zeekstd_b200.h).
+// Owns the CUDA streams, events, pinned/HBM staging and the per-slot codec workspaces.
+#pragma once
+#include "zk_decode.h"
+#include "zk_encode.h"
+
+#define ZK_SLOTS 3                        // pipeline depth of the host<->device paths (H2D | kernels | D2H overlap)
+
+struct ZkSlot {
+    cudaStream_t stream = nullptr;
+    ZkDecodeWs dws;
+    ZkEncodeWs ews;
+    uint8_t* d_in = nullptr; size_t cap_in = 0;      // device staging for the host-pointer entry points
+    uint8_t* d_out = nullptr; size_t cap_out = 0;
+};
+
+struct zk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    ZkSlot slot[ZK_SLOTS];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    unsigned long long launches() const {
+        unsigned long long n = 0;
+        for (int i = 0; i < ZK_SLOTS; i++) n += slot[i].dws.launches + slot[i].ews.launches;
+        return n;
+    }
+};
+
+int zk_slot_ensure(ZkSlot* s, size_t need_in, size_t need_out);

@@ -1,0 +1,41 @@
+// zk_decode.h -- host-visible interface of the batched decode path (zk_decode.cu).
+#pragma once
+#include "zk_common.cuh"
+#include <string.h>
+
+struct ZkDecodeArgs {                 // kernel parameter block (by value)
+    const uint8_t* comp;              // compressed bytes; entry e occupies [c_off[e], c_off[e+1])
+    const unsigned long long* c_off;  // device, n_entries + 1
+    const unsigned long long* d_off;  // device, n_entries + 1; entry e decodes to dst + d_off[e]
+    uint8_t* dst;
+    uint32_t n_entries;
+    ZkBlock* blocks; ZkEntry* entries; ZkCounters* counters; uint32_t* work_counter;
+    uint8_t* lit; uint32_t* seq_lit_end; uint32_t* seq_out_end; uint32_t* seq_off;
+    unsigned long long cap_blocks, cap_lit, cap_seq;
+};
+
+struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on demand, reused across batches
+    ZkBlock* blocks = nullptr; size_t cap_blocks = 0;
+    ZkEntry* entries = nullptr; size_t cap_entries = 0;
+    ZkCounters* counters = nullptr;
+    uint8_t* lit = nullptr; size_t cap_lit = 0;
+    uint32_t* seq_lit_end = nullptr; uint32_t* seq_out_end = nullptr; uint32_t* seq_off = nullptr; size_t cap_seq = 0;
+    uint64_t* c_off = nullptr; uint64_t* d_off = nullptr;
+    ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
+    size_t want_blocks = 0, want_lit = 0, want_seq = 0;   // exact needs reported by a batch that overflowed
+    uint32_t pending_n = 0;
+    int sm_count = 0;
+    unsigned long long launches = 0;  // kernels launched so far (bench.py's gpu_launches)
+};
+
+// Decode n seek-table entries.  d_comp / d_dst are device pointers (16-byte aligned, 16 readable bytes of
+// padding after the last byte); c_off / d_off are HOST arrays of n+1 cumulative offsets relative to those
+// pointers (seek_table.rs:97-101).  status_out[n] (host, optional) receives 0 or -(zstd code) per entry.
+// Returns 0, or the first non-zero entry status, or -(code) for a launch/allocation failure.
+// Synchronous with respect to `stream` on return.
+int zk_decode_batch(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp, const uint64_t* c_off, const uint64_t* d_off,
+                    uint32_t n, uint8_t* d_dst, int verify_checksum, int32_t* status_out, int exec_warps);
+int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp, const uint64_t* c_off, const uint64_t* d_off,
+                      uint32_t n, uint8_t* d_dst, int verify_checksum, int exec_warps);
+int zk_decode_collect(ZkDecodeWs* ws, cudaStream_t stream, int32_t* status_out);
+void zk_decode_ws_free(ZkDecodeWs* ws);
