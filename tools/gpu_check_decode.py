@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import oracle as O
 from zeekstd_b200 import corpus, _native as N
 
-lib = N.load()
+lib = N.load(require_all=False)
 ctx = ctypes.c_void_p()
 rc = lib.zk_ctx_create(0, 0, ctypes.byref(ctx)); assert rc == 0, rc
 print(lib.zk_version(), torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)

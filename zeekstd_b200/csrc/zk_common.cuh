@@ -61,7 +61,8 @@ struct ZkBlock {                 // one zstd block of one seek-table entry
     uint32_t lit_size;           // regenerated literal bytes                  [scan kernel]
     uint32_t lit_src;            // raw literals: offset rel. to entry start   [entropy kernel]
     uint32_t regen;              // regenerated block size                     [entropy kernel]
-    int32_t status;              // 0 or -(zstd code)                          [entropy kernel]
+    int32_t status;              // sequences: 0 or -(zstd code)               [seq kernel]
+    int32_t lit_status;          // literals:  0 or -(zstd code)               [huf kernel]
     int32_t huf_ref;             // block index whose Huffman tree a Treeless block reuses (-1 none)
     int32_t ll_ref, of_ref, ml_ref;   // block index defining the table a Repeat mode reuses (-1 none)
     uint32_t rep_out[3];         // rep-offset state after this block: concrete value, or ZK_SYM|slot<<28|delta
@@ -92,6 +93,7 @@ struct ZkCounters {
     unsigned long long n_blocks, n_lit, n_seq;   // exact needs (accumulated even when over capacity)
     uint32_t overflow;
     uint32_t n_errors;
+    uint32_t n_huf_blocks, n_seq_blocks;         // lengths of huf_list / seq_list
 };
 
 // -------------------------------------------------------------------------------------------

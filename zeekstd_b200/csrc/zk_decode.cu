@@ -6,8 +6,9 @@
 // seekable format, seekable_format.md:23-29):
 //
 //   K-D0 zk_scan_kernel     one thread / entry : walk frame + block headers, carve scratch
-//   K-D1 zk_entropy_kernel  one CTA   / block  : Huffman literals (warp 1) + FSE sequences (warp 0)
-//   K-D2 zk_exec_kernel     one CTA   / entry  : ordered sequence execution, W warps pipelined
+//   K-D1s zk_seq_kernel     one LANE  / block  : FSE sequence decode (tables + state machine in smem)
+//   K-D1h zk_huf_kernel     one LANE  / stream : Huffman literal decode (4 lanes per 4-stream block)
+//   K-D2 zk_exec_kernel     one CTA   / entry  : ordered sequence execution through a shared-memory window
 //   K-D3 zk_xxh64_kernel    one warp  / entry  : content checksum (only if requested & present)
 //
 // Format rules: RFC 8878 as restated in SURVEY.md Appendix A (the arithmetic is not in the
@@ -20,7 +21,7 @@
 // =============================================================================================
 struct ZkBlkInfo {
     uint32_t src, size; uint8_t type, flags;
-    uint32_t lit_size, nseq; uint8_t lit_type, modes; uint64_t fcs;
+    uint32_t lit_size, nseq; uint8_t lit_type, modes, lit_hdr; uint64_t fcs;
 };
 
 struct ZkLitHdr { uint32_t type, hdr, regen, comp, streams; };
@@ -105,7 +106,7 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
             bi.src = pos + 3; bi.size = bsize; bi.type = (uint8_t)type;
             bi.flags = (uint8_t)((first ? ZKB_FIRST : 0) | (last ? ZKB_LAST : 0) | ((last && csum) ? ZKB_HAS_CSUM : 0) |
                                  ((last && fcs_sz) ? ZKB_HAS_FCS : 0));
-            bi.fcs = fcs; bi.lit_size = 0; bi.nseq = 0; bi.lit_type = 0; bi.modes = 0;
+            bi.fcs = fcs; bi.lit_size = 0; bi.nseq = 0; bi.lit_type = 0; bi.modes = 0; bi.lit_hdr = 0;
             if (type == 2) {
                 const uint8_t* b = p + pos + 3;
                 if (bsize < 2) return ZKZ_CORRUPTION;
@@ -123,7 +124,7 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
                     bi.modes = b[lsec + sh];
                     if (bi.modes & 3) return ZKZ_CORRUPTION;
                 }
-                bi.lit_size = lh.regen; bi.nseq = nseq; bi.lit_type = (uint8_t)lh.type;
+                bi.lit_size = lh.regen; bi.nseq = nseq; bi.lit_type = (uint8_t)lh.type; bi.lit_hdr = (uint8_t)lh.hdr;
             }
             int rc = emit(bi);
             if (rc) return rc;
@@ -137,22 +138,25 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
 }
 
 struct ZkCountEmit {
-    uint32_t nb = 0, nlit = 0, nseq = 0;
+    uint32_t nb = 0, nlit = 0, nseq = 0, nhuf = 0, nsqb = 0;
     __device__ int operator()(const ZkBlkInfo& bi) {
         nb++;
-        if (bi.type == 2) { if (bi.lit_type >= 2) nlit += (bi.lit_size + 15u) & ~15u; nseq += bi.nseq; }
+        if (bi.type == 2) {
+            if (bi.lit_type >= 2) { nlit += (bi.lit_size + 15u) & ~15u; nhuf++; }
+            nseq += bi.nseq; nsqb += bi.nseq != 0;
+        }
         return 0;
     }
 };
 
 struct ZkFillEmit {
-    ZkBlock* blocks; uint32_t entry, bidx, lit, seq;
+    ZkBlock* blocks; const uint8_t* ebase; uint32_t* huf_list; uint32_t* seq_list; uint32_t entry, bidx, lit, seq, hufi, sqbi;
     int32_t huf_ref = -1, ll_ref = -1, of_ref = -1, ml_ref = -1;
     __device__ int operator()(const ZkBlkInfo& bi) {
         ZkBlock b;
         b.src = bi.src; b.size = bi.size; b.entry = entry; b.type = bi.type; b.flags = bi.flags;
         b.lit_kind = 0; b.lit_byte = 0; b.lit_base = lit; b.seq_base = seq; b.nseq = bi.nseq; b.lit_size = bi.lit_size;
-        b.lit_src = 0; b.regen = bi.type == 2 ? 0 : bi.size; b.status = 0;
+        b.lit_src = 0; b.regen = bi.type == 2 ? 0 : bi.size; b.status = 0; b.lit_status = 0;
         b.rep_out[0] = ZK_SYM_MAKE(0, 0); b.rep_out[1] = ZK_SYM_MAKE(1, 0); b.rep_out[2] = ZK_SYM_MAKE(2, 0);
         b.fcs = bi.fcs; b.hash_start = 0; b.hash_len = 0;
         if (bi.flags & ZKB_FIRST) { huf_ref = ll_ref = of_ref = ml_ref = -1; }
@@ -160,8 +164,12 @@ struct ZkFillEmit {
         if (bi.type == 2) {
             if (bi.lit_type == 3) { if (huf_ref < 0) return ZKZ_CORRUPTION; b.huf_ref = huf_ref; }
             if (bi.lit_type == 2) huf_ref = (int32_t)bidx;
-            if (bi.lit_type >= 2) lit += (bi.lit_size + 15u) & ~15u;
+            if (bi.lit_type >= 2) { lit += (bi.lit_size + 15u) & ~15u; b.lit_kind = 2; huf_list[hufi++] = bidx; }
+            else if (bi.lit_type == 0) { b.lit_kind = 0; b.lit_src = bi.src + bi.lit_hdr; }
+            else { b.lit_kind = 1; b.lit_byte = ebase[bi.src + bi.lit_hdr]; }
+            if (bi.nseq == 0) b.regen = bi.lit_size;         // literals-only block
             if (bi.nseq) {
+                seq_list[sqbi++] = bidx;
                 uint32_t ml_m = (bi.modes >> 2) & 3, of_m = (bi.modes >> 4) & 3, ll_m = (bi.modes >> 6) & 3;
                 if (ll_m == 3) { if (ll_ref < 0) return ZKZ_CORRUPTION; b.ll_ref = ll_ref; } else ll_ref = (int32_t)bidx;
                 if (of_m == 3) { if (of_ref < 0) return ZKZ_CORRUPTION; b.of_ref = of_ref; } else of_ref = (int32_t)bidx;
@@ -187,11 +195,13 @@ __global__ void __launch_bounds__(128) zk_scan_kernel(ZkDecodeArgs a) {
     unsigned long long b0 = atomicAdd(&a.counters->n_blocks, (unsigned long long)ce.nb);
     unsigned long long l0 = atomicAdd(&a.counters->n_lit, (unsigned long long)ce.nlit);
     unsigned long long s0 = atomicAdd(&a.counters->n_seq, (unsigned long long)ce.nseq);
+    uint32_t h0 = atomicAdd(&a.counters->n_huf_blocks, ce.nhuf), q0 = atomicAdd(&a.counters->n_seq_blocks, ce.nsqb);
     if (b0 + ce.nb > a.cap_blocks || l0 + ce.nlit > a.cap_lit || s0 + ce.nseq > a.cap_seq) {
         atomicOr(&a.counters->overflow, 1u);
         ent.status = ZK_ST_RETRY; a.entries[e] = ent; return;
     }
     ZkFillEmit fe; fe.blocks = a.blocks; fe.entry = e; fe.bidx = (uint32_t)b0; fe.lit = (uint32_t)l0; fe.seq = (uint32_t)s0;
+    fe.ebase = p; fe.huf_list = a.huf_list; fe.seq_list = a.seq_list; fe.hufi = h0; fe.sqbi = q0;   // lists have cap_blocks entries
     rc = zk_walk_entry(p, n, fe);
     ent.first_block = (uint32_t)b0; ent.n_blocks = ce.nb;
     if (rc) { ent.status = -rc; ent.n_blocks = 0; atomicAdd(&a.counters->n_errors, 1u); }
@@ -199,30 +209,27 @@ __global__ void __launch_bounds__(128) zk_scan_kernel(ZkDecodeArgs a) {
 }
 
 // =============================================================================================
-// K-D1: per-block entropy decode
+// K-D1s: FSE sequence decode -- one LANE per zstd block.
+//
+// A sequence bitstream is one serial dependency chain (three interleaved FSE states sharing one
+// backward bit cursor, A.5), so the only parallelism is across blocks.  Profiling the first version
+// (one block per CTA, one active lane per warp) showed the SMs issue-bound at 1/32 SIMT efficiency;
+// here every lane of a warp runs the identical decode loop over ITS OWN block with ITS OWN tables
+// in shared memory, so one issued instruction advances up to ZK_SEQ_LANES chains.
 // =============================================================================================
-#define ZK_D1_THREADS 64
+#define ZK_SEQ_LANES 9            // 9 x 11.7 KiB of tables per warp-CTA -> 2 CTAs / SM
 
-struct ZkD1Smem {
+struct ZkSeqSlot {
     ZkSeqCell ll[512], ml[512], of[256];       // 10 KiB
-    uint16_t huf[2048];                        // (nbBits << 8) | symbol, 4 KiB
     int16_t cnt[3][64];
-    uint8_t symof[3][512];
-    uint16_t nxt[3][64];
-    uint8_t weights[256];
-    uint16_t hpos[256];
-    uint8_t wsym[64], wnb[64]; uint16_t wbase[64];   // FSE table for Huffman weights (log <= 6)
-    int tbl_log[3], tbl_nsym[3], tbl_mode[3];   // mode: 0 counts, 1 rle (cnt[t][0] = symbol)
-    uint32_t bits_off;                          // offset of the sequence bitstream inside the block
-    int huf_bits;
-    int st_lit, st_seq;
-    uint32_t work;
+    uint16_t nxt[64];
+    uint8_t symof[512];
+    int tbl_log[3], tbl_nsym[3], tbl_mode[3];  // mode: 0 = counts in cnt[t], 1 = RLE (cnt[t][0] = symbol)
 };
 
-// Locate the three table descriptions of a block (A.5).  desc_off[t] = offset of table t's description
-// inside the block content; also parses FSE counts when `want[t]` (into sm.cnt[t]).  t: 0 LL, 1 OF, 2 ML.
-// Returns 0 or a zstd code.  *bits_off = start of the bitstream.
-__device__ int zk_locate_seq_tables(ZkD1Smem& sm, const uint8_t* b, uint32_t bsize, const bool want[3], uint32_t* bits_off) {
+// Locate the three table descriptions of a block (A.5) and parse those that are wanted into sl.cnt[t]
+// (t: 0 LL, 1 OF, 2 ML).  Returns 0 or a zstd code.  *bits_off = start of the sequence bitstream.
+__device__ int zk_locate_seq_tables(ZkSeqSlot& sl, const uint8_t* b, uint32_t bsize, bool w0, bool w1, bool w2, uint32_t* bits_off) {
     ZkLitHdr lh;
     if (!zk_parse_lit_hdr(b, bsize, lh)) return ZKZ_CORRUPTION;
     uint32_t lsec = zk_lit_section_size(lh);
@@ -230,32 +237,33 @@ __device__ int zk_locate_seq_tables(ZkD1Smem& sm, const uint8_t* b, uint32_t bsi
     uint32_t nseq, sh = zk_parse_nseq(b + lsec, bsize - lsec, nseq);
     if (!sh || nseq == 0 || lsec + sh >= bsize) return ZKZ_CORRUPTION;
     uint32_t modes = b[lsec + sh], pos = lsec + sh + 1;
-    const int max_log[3] = {9, 8, 9}, max_sym[3] = {35, 31, 52};
     for (int t = 0; t < 3; t++) {
+        const bool want = t == 0 ? w0 : (t == 1 ? w1 : w2);
+        const int max_log = t == 1 ? 8 : 9, max_sym = t == 0 ? 35 : (t == 1 ? 31 : 52);
         uint32_t m = (modes >> (6 - 2 * t)) & 3;
         if (m == 0) {
-            if (want[t]) {
-                sm.tbl_mode[t] = 0;
-                if (t == 0) { for (int i = 0; i < 36; i++) sm.cnt[0][i] = ZK_LL_DEFAULT[i]; sm.tbl_nsym[0] = 36; sm.tbl_log[0] = 6; }
-                else if (t == 1) { for (int i = 0; i < 29; i++) sm.cnt[1][i] = ZK_OF_DEFAULT[i]; sm.tbl_nsym[1] = 29; sm.tbl_log[1] = 5; }
-                else { for (int i = 0; i < 53; i++) sm.cnt[2][i] = ZK_ML_DEFAULT[i]; sm.tbl_nsym[2] = 53; sm.tbl_log[2] = 6; }
+            if (want) {
+                sl.tbl_mode[t] = 0;
+                if (t == 0) { for (int i = 0; i < 36; i++) sl.cnt[0][i] = ZK_LL_DEFAULT[i]; sl.tbl_nsym[0] = 36; sl.tbl_log[0] = 6; }
+                else if (t == 1) { for (int i = 0; i < 29; i++) sl.cnt[1][i] = ZK_OF_DEFAULT[i]; sl.tbl_nsym[1] = 29; sl.tbl_log[1] = 5; }
+                else { for (int i = 0; i < 53; i++) sl.cnt[2][i] = ZK_ML_DEFAULT[i]; sl.tbl_nsym[2] = 53; sl.tbl_log[2] = 6; }
             }
         } else if (m == 1) {
             if (pos >= bsize) return ZKZ_CORRUPTION;
-            if (want[t]) {
-                if (b[pos] > max_sym[t]) return ZKZ_CORRUPTION;
-                sm.tbl_mode[t] = 1; sm.cnt[t][0] = b[pos]; sm.tbl_log[t] = 0; sm.tbl_nsym[t] = 1;
+            if (want) {
+                if (b[pos] > max_sym) return ZKZ_CORRUPTION;
+                sl.tbl_mode[t] = 1; sl.cnt[t][0] = b[pos]; sl.tbl_log[t] = 0; sl.tbl_nsym[t] = 1;
             }
             pos += 1;
         } else if (m == 2) {
-            int16_t scratch[64];
             int ns, lg;
-            uint32_t used = zk_fse_read_ncount(b + pos, bsize - pos, max_log[t], max_sym[t], want[t] ? sm.cnt[t] : scratch, &ns, &lg);
+            // an unwanted table is parsed into the (not yet used) nxt/symof scratch just to learn its length
+            uint32_t used = zk_fse_read_ncount(b + pos, bsize - pos, max_log, max_sym, want ? sl.cnt[t] : (int16_t*)sl.symof, &ns, &lg);
             if (!used) return ZKZ_CORRUPTION;
-            if (want[t]) { sm.tbl_mode[t] = 0; sm.tbl_nsym[t] = ns; sm.tbl_log[t] = lg; }
+            if (want) { sl.tbl_mode[t] = 0; sl.tbl_nsym[t] = ns; sl.tbl_log[t] = lg; }
             pos += used;
         } else {
-            if (want[t]) return ZKZ_CORRUPTION;   // caller resolves Repeat through *_ref first
+            if (want) return ZKZ_CORRUPTION;   // Repeat is resolved through *_ref by the caller
         }
     }
     if (pos > bsize) return ZKZ_CORRUPTION;
@@ -263,11 +271,11 @@ __device__ int zk_locate_seq_tables(ZkD1Smem& sm, const uint8_t* b, uint32_t bsi
     return 0;
 }
 
-// Build one sequence decoding table from sm.cnt[t] (A.6).  Executed by lanes 0..2 of warp 0 in parallel.
-__device__ int zk_build_seq_table(ZkD1Smem& sm, int t) {
-    ZkSeqCell* cell = t == 0 ? sm.ll : (t == 1 ? sm.of : sm.ml);
-    if (sm.tbl_mode[t] == 1) {
-        int s = sm.cnt[t][0];
+// Build one sequence decoding table from sl.cnt[t] (A.6).
+__device__ int zk_build_seq_table(ZkSeqSlot& sl, int t) {
+    ZkSeqCell* cell = t == 0 ? sl.ll : (t == 1 ? sl.of : sl.ml);
+    if (sl.tbl_mode[t] == 1) {
+        int s = sl.cnt[t][0];
         ZkSeqCell c; c.next_base = 0; c.nb_bits = 0;
         if (t == 0) { c.base_value = ZK_LL_BASE[s]; c.add_bits = ZK_LL_BITS[s]; }
         else if (t == 1) { c.base_value = 1u << s; c.add_bits = (uint8_t)s; }
@@ -275,8 +283,8 @@ __device__ int zk_build_seq_table(ZkD1Smem& sm, int t) {
         cell[0] = c;
         return 0;
     }
-    int log = sm.tbl_log[t], S = 1 << log, nsym = sm.tbl_nsym[t], high = S - 1;
-    uint8_t* symof = sm.symof[t]; uint16_t* nxt = sm.nxt[t]; const int16_t* cnt = sm.cnt[t];
+    int log = sl.tbl_log[t], S = 1 << log, nsym = sl.tbl_nsym[t], high = S - 1;
+    uint8_t* symof = sl.symof; uint16_t* nxt = sl.nxt; const int16_t* cnt = sl.cnt[t];
     for (int s = 0; s < nsym; s++) {
         if (cnt[s] == -1) { symof[high--] = (uint8_t)s; nxt[s] = 1; }
         else nxt[s] = (uint16_t)cnt[s];
@@ -302,31 +310,129 @@ __device__ int zk_build_seq_table(ZkD1Smem& sm, int t) {
     return 0;
 }
 
-// Huffman tree description -> sm.weights[0..nw) incl. the implied last weight (A.4).  Lane 0 only.
-// Returns bytes consumed or 0 on corruption; sets sm.huf_bits.
-__device__ uint32_t zk_read_huf_weights(ZkD1Smem& sm, const uint8_t* p, uint32_t n, int* nw_out) {
+// Decode all sequences of one block (lane-local).  Returns 0 or a zstd code.
+__device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkDecodeArgs& a, const ZkBlock& blk, uint32_t bidx, const uint8_t* ebase) {
+    const uint8_t* b = ebase + blk.src;
+    uint32_t bits_off = 0;
+    int st = zk_locate_seq_tables(sl, b, blk.size, blk.ll_ref < 0, blk.of_ref < 0, blk.ml_ref < 0, &bits_off);
+    if (st) return st;
+    if (blk.ll_ref >= 0) { const ZkBlock& rb = a.blocks[blk.ll_ref]; uint32_t d; if ((st = zk_locate_seq_tables(sl, ebase + rb.src, rb.size, true, false, false, &d))) return st; }
+    if (blk.of_ref >= 0) { const ZkBlock& rb = a.blocks[blk.of_ref]; uint32_t d; if ((st = zk_locate_seq_tables(sl, ebase + rb.src, rb.size, false, true, false, &d))) return st; }
+    if (blk.ml_ref >= 0) { const ZkBlock& rb = a.blocks[blk.ml_ref]; uint32_t d; if ((st = zk_locate_seq_tables(sl, ebase + rb.src, rb.size, false, false, true, &d))) return st; }
+    for (int t = 0; t < 3; t++) if ((st = zk_build_seq_table(sl, t))) return st;
+
+    ZkBackBits br;
+    if (!br.init(b + bits_off, blk.size - bits_off)) return ZKZ_CORRUPTION;
+    const int ll_log = sl.tbl_log[0], of_log = sl.tbl_log[1], ml_log = sl.tbl_log[2];
+    br.refill();
+    uint32_t s_l = br.read(ll_log), s_o = br.read(of_log), s_m = br.read(ml_log);
+    uint32_t r0 = ZK_SYM_MAKE(0, 0), r1 = ZK_SYM_MAKE(1, 0), r2 = ZK_SYM_MAKE(2, 0);
+    uint32_t lit_end = 0, out_end = 0;
+    uint32_t* o_lit = a.seq_lit_end + blk.seq_base;
+    uint32_t* o_out = a.seq_out_end + blk.seq_base;
+    uint32_t* o_off = a.seq_off + blk.seq_base;
+    const uint32_t nseq = blk.nseq;
+    for (uint32_t i = 0; i < nseq; i++) {
+        ZkSeqCell cl = sl.ll[s_l], co = sl.of[s_o], cm = sl.ml[s_m];
+        br.refill();                                                  // <= 31 + 16 + 16 bits follow
+        uint32_t ofv = co.base_value + br.read(co.add_bits);
+        uint32_t mlv = cm.base_value + br.read(cm.add_bits);
+        uint32_t llv = cl.base_value + br.read(cl.add_bits);
+        br.refill();                                                  // <= 9 + 9 + 8 bits follow
+        if (i + 1 < nseq) {
+            s_l = cl.next_base + br.read(cl.nb_bits);
+            s_m = cm.next_base + br.read(cm.nb_bits);
+            s_o = co.next_base + br.read(co.nb_bits);
+        }
+        // repeat-offset history, kept symbolic w.r.t. the (unknown) state entering this block
+        uint32_t off;
+        if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
+        else {
+            uint32_t idx = ofv - 1 + (llv == 0);
+            if (idx == 0) off = r0;
+            else {
+                if (idx == 3) {
+                    if (r0 & ZK_SYM) off = r0 + 1;                    // delta + 1
+                    else { off = r0 - 1; if (off == 0) st = ZKZ_CORRUPTION; }
+                } else off = idx == 1 ? r1 : r2;
+                if (idx != 1) r2 = r1;
+                r1 = r0; r0 = off;
+            }
+        }
+        lit_end += llv; out_end += llv + mlv;
+        o_lit[i] = lit_end; o_out[i] = out_end; o_off[i] = off;
+    }
+    if (br.bp != 0) st = ZKZ_CORRUPTION;
+    if (lit_end > blk.lit_size) st = ZKZ_CORRUPTION;
+    else if (out_end + (blk.lit_size - lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
+    a.blocks[bidx].rep_out[0] = r0; a.blocks[bidx].rep_out[1] = r1; a.blocks[bidx].rep_out[2] = r2;
+    a.blocks[bidx].regen = out_end + (blk.lit_size - lit_end);
+    return st;
+}
+
+__global__ void __launch_bounds__(32) zk_seq_kernel(ZkDecodeArgs a) {
+    ZK_DYN_SMEM(smem);
+    ZkSeqSlot* slots = (ZkSeqSlot*)smem;
+    const int lane = threadIdx.x;
+    if (a.counters->overflow) return;
+    const uint32_t n = a.counters->n_seq_blocks;
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&a.work_counter[0], 1u);
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        uint32_t first = g * ZK_SEQ_LANES;
+        if (first >= n) break;
+        uint32_t my = first + lane;
+        if (lane < ZK_SEQ_LANES && my < n) {
+            uint32_t bidx = a.seq_list[my];
+            ZkBlock blk = a.blocks[bidx];
+            if (a.entries[blk.entry].status == 0) {
+                int st = zk_decode_block_sequences(slots[lane], a, blk, bidx, a.comp + a.c_off[blk.entry]);
+                a.blocks[bidx].status = st ? -st : 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
+// K-D1h: Huffman literal decode -- one LANE per Huffman stream (4 lanes per 4-stream block).
+// =============================================================================================
+#define ZK_HUF_SLOTS 8            // blocks per warp-CTA; 8 x 5.2 KiB -> 5 CTAs / SM
+
+struct ZkHufSlot {
+    uint16_t tbl[2048];                        // (nbBits << 8) | symbol
+    uint8_t weights[256];
+    uint16_t hpos[256];
+    uint8_t wsym[64], wnb[64]; uint16_t wbase[64];   // FSE table for compressed weights (log <= 6)
+    int huf_bits, nw, st;
+    uint32_t tree_bytes;
+};
+
+// Huffman tree description -> sl.weights[0..nw) incl. the implied last weight (A.4).
+// Returns bytes consumed or 0 on corruption; sets sl.huf_bits / sl.nw.
+__device__ uint32_t zk_read_huf_weights(ZkHufSlot& sl, const uint8_t* p, uint32_t n) {
     if (n < 1) return 0;
     uint32_t hb = p[0], used; int nw = 0;
     if (hb >= 128) {
         nw = (int)hb - 127; used = 1 + (uint32_t)(nw + 1) / 2;
         if (used > n) return 0;
-        for (int i = 0; i < nw; i++) { uint32_t b = p[1 + i / 2]; sm.weights[i] = (uint8_t)((i & 1) ? (b & 15) : (b >> 4)); }
+        for (int i = 0; i < nw; i++) { uint32_t b = p[1 + i / 2]; sl.weights[i] = (uint8_t)((i & 1) ? (b & 15) : (b >> 4)); }
     } else {
         used = 1 + hb;
         if (hb == 0 || used > n) return 0;
         int16_t cnt[16]; int ns, lg;
         uint32_t r = zk_fse_read_ncount(p + 1, hb, 6, 12, cnt, &ns, &lg);
         if (!r) return 0;
-        // small FSE table (A.6)
         int S = 1 << lg, high = S - 1; uint16_t nx[16];
-        for (int s = 0; s < ns; s++) { if (cnt[s] == -1) { sm.wsym[high--] = (uint8_t)s; nx[s] = 1; } else nx[s] = (uint16_t)cnt[s]; }
+        for (int s = 0; s < ns; s++) { if (cnt[s] == -1) { sl.wsym[high--] = (uint8_t)s; nx[s] = 1; } else nx[s] = (uint16_t)cnt[s]; }
         int step = (S >> 1) + (S >> 3) + 3, pos = 0;
         for (int s = 0; s < ns; s++)
-            for (int q = 0; q < cnt[s]; q++) { sm.wsym[pos] = (uint8_t)s; do { pos = (pos + step) & (S - 1); } while (pos > high); }
+            for (int q = 0; q < cnt[s]; q++) { sl.wsym[pos] = (uint8_t)s; do { pos = (pos + step) & (S - 1); } while (pos > high); }
         if (pos != 0) return 0;
         for (int u = 0; u < S; u++) {
-            int s = sm.wsym[u]; uint32_t x = nx[s]++; int nb = lg - zk_highbit(x);
-            sm.wnb[u] = (uint8_t)nb; sm.wbase[u] = (uint16_t)((x << nb) - S);
+            int s = sl.wsym[u]; uint32_t x = nx[s]++; int nb = lg - zk_highbit(x);
+            sl.wnb[u] = (uint8_t)nb; sl.wbase[u] = (uint16_t)((x << nb) - S);
         }
         ZkBackBits br;
         if (!br.init(p + 1 + r, hb - r)) return 0;
@@ -336,17 +442,17 @@ __device__ uint32_t zk_read_huf_weights(ZkD1Smem& sm, const uint8_t* p, uint32_t
         for (;;) {   // two interleaved states, over-read terminates (A.4)
             if (nw >= 254) return 0;
             br.refill();
-            sm.weights[nw++] = sm.wsym[s1];
-            s1 = sm.wbase[s1] + br.read(sm.wnb[s1]);
-            if (br.bp < 0) { sm.weights[nw++] = sm.wsym[s2]; break; }
-            sm.weights[nw++] = sm.wsym[s2];
-            s2 = sm.wbase[s2] + br.read(sm.wnb[s2]);
-            if (br.bp < 0) { sm.weights[nw++] = sm.wsym[s1]; break; }
+            sl.weights[nw++] = sl.wsym[s1];
+            s1 = sl.wbase[s1] + br.read(sl.wnb[s1]);
+            if (br.bp < 0) { sl.weights[nw++] = sl.wsym[s2]; break; }
+            sl.weights[nw++] = sl.wsym[s2];
+            s2 = sl.wbase[s2] + br.read(sl.wnb[s2]);
+            if (br.bp < 0) { sl.weights[nw++] = sl.wsym[s1]; break; }
         }
     }
     uint32_t total = 0, n_w1 = 0;
     for (int i = 0; i < nw; i++) {
-        uint32_t w = sm.weights[i];
+        uint32_t w = sl.weights[i];
         if (w > 11) return 0;
         if (w) total += 1u << (w - 1);
         n_w1 += (w == 1);
@@ -357,11 +463,10 @@ __device__ uint32_t zk_read_huf_weights(ZkD1Smem& sm, const uint8_t* p, uint32_t
     uint32_t left = (1u << max_bits) - total;
     if (left & (left - 1)) return 0;               // must be a power of two (left >= 1 by construction)
     uint32_t lw = (uint32_t)zk_highbit(left) + 1;
-    sm.weights[nw++] = (uint8_t)lw;
+    sl.weights[nw++] = (uint8_t)lw;
     n_w1 += (lw == 1);
     if (n_w1 < 2 || (n_w1 & 1)) return 0;          // libzstd's HUF_readStats sanity rule
-    sm.huf_bits = max_bits;
-    *nw_out = nw;
+    sl.huf_bits = max_bits; sl.nw = nw;
     return used;
 }
 
@@ -389,197 +494,126 @@ __device__ bool zk_huf_decode_stream(const uint16_t* tbl, int max_bits, const ui
     return br.bp == 0;
 }
 
-__device__ void zk_d1_literals(ZkD1Smem& sm, const ZkDecodeArgs& a, ZkBlock& blk, uint32_t bidx, const uint8_t* ebase, int lane) {
-    const uint8_t* b = ebase + blk.src;
-    ZkLitHdr lh;
-    zk_parse_lit_hdr(b, blk.size, lh);        // validated by the scan kernel
-    if (lh.type == 0) {
-        if (lane == 0) { a.blocks[bidx].lit_kind = 0; a.blocks[bidx].lit_src = blk.src + lh.hdr; sm.st_lit = 0; }
-        return;
-    }
-    if (lh.type == 1) {
-        if (lane == 0) { a.blocks[bidx].lit_kind = 1; a.blocks[bidx].lit_byte = b[lh.hdr]; sm.st_lit = 0; }
-        return;
-    }
-    // Huffman-compressed: find the tree description (own block, or the block a Treeless block refers to)
-    const uint8_t* q = b + lh.hdr; uint32_t qn = lh.comp;
-    int nw = 0; uint32_t tree_bytes = 0;
-    if (lane == 0) {
-        int st = 0;
-        if (lh.type == 2) {
-            tree_bytes = zk_read_huf_weights(sm, q, qn, &nw);
-            if (!tree_bytes) st = ZKZ_CORRUPTION;
-        } else {
-            const ZkBlock& rb = a.blocks[blk.huf_ref];
-            const uint8_t* r = ebase + rb.src;
-            ZkLitHdr rh;
-            zk_parse_lit_hdr(r, rb.size, rh);
-            if (!zk_read_huf_weights(sm, r + rh.hdr, rh.comp, &nw)) st = ZKZ_CORRUPTION;
-        }
-        if (!st) {   // start cell of every symbol: weight ascending, symbols in natural order
-            uint32_t rank_start[13]; uint32_t cntw[13];
-            for (int w = 0; w < 13; w++) cntw[w] = 0;
-            for (int s = 0; s < nw; s++) cntw[sm.weights[s]]++;
-            uint32_t acc = 0;
-            for (int w = 1; w <= sm.huf_bits; w++) { rank_start[w] = acc; acc += cntw[w] << (w - 1); }
-            for (int s = 0; s < nw; s++) { int w = sm.weights[s]; if (w) { sm.hpos[s] = (uint16_t)rank_start[w]; rank_start[w] += 1u << (w - 1); } }
-            if (acc != (1u << sm.huf_bits)) st = ZKZ_CORRUPTION;
-        }
-        sm.st_lit = st;
-    }
-    __syncwarp();
-    nw = __shfl_sync(0xFFFFFFFFu, nw, 0);
-    tree_bytes = __shfl_sync(0xFFFFFFFFu, tree_bytes, 0);
-    if (sm.st_lit) return;
-    int max_bits = sm.huf_bits;
-    for (int s = lane; s < nw; s += 32) {
-        int w = sm.weights[s];
-        if (!w) continue;
-        uint32_t len = 1u << (w - 1), pos = sm.hpos[s];
-        uint16_t e = (uint16_t)(((max_bits + 1 - w) << 8) | s);
-        for (uint32_t i = 0; i < len; i++) sm.huf[pos + i] = e;
-    }
-    __syncwarp();
-    q += tree_bytes; qn -= tree_bytes;
-    uint8_t* out = a.lit + blk.lit_base;
-    bool ok = true;
-    if (lh.streams == 1) {
-        if (lane == 0) ok = zk_huf_decode_stream(sm.huf, max_bits, q, qn, out, lh.regen);
-    } else {
-        uint32_t seg = (lh.regen + 3) / 4;
-        if (qn < 10 || lh.regen < 6 || seg * 3 > lh.regen) ok = false;   // 6-byte jump table + 4 non-empty streams; libzstd rejects regen < 6
-        else {
-            uint32_t s1 = zk_ld_le16(q), s2 = zk_ld_le16(q + 2), s3 = zk_ld_le16(q + 4);
-            if (6 + s1 + s2 + s3 >= qn) ok = false;
-            else if (lane < 4) {
-                uint32_t s4 = qn - 6 - s1 - s2 - s3;
-                uint32_t off = lane == 0 ? 0 : (lane == 1 ? s1 : (lane == 2 ? s1 + s2 : s1 + s2 + s3));
-                uint32_t len = lane == 0 ? s1 : (lane == 1 ? s2 : (lane == 2 ? s3 : s4));
-                uint32_t cnt = lane < 3 ? seg : lh.regen - 3 * seg;
-                ok = zk_huf_decode_stream(sm.huf, max_bits, q + 6 + off, len, out + lane * seg, cnt);
-            }
-        }
-    }
-    uint32_t bad = __ballot_sync(0xFFFFFFFFu, !ok);
-    if (lane == 0) {
-        a.blocks[bidx].lit_kind = 2;
-        if (bad) sm.st_lit = ZKZ_CORRUPTION;
-    }
-}
-
-__device__ void zk_d1_sequences(ZkD1Smem& sm, const ZkDecodeArgs& a, ZkBlock& blk, uint32_t bidx, const uint8_t* ebase, int lane) {
-    const uint8_t* b = ebase + blk.src;
-    if (blk.nseq == 0) { if (lane == 0) sm.st_seq = 0; return; }
-    if (lane == 0) {
-        int st = 0;
-        bool want[3] = { blk.ll_ref < 0, blk.of_ref < 0, blk.ml_ref < 0 };
-        uint32_t bits_off = 0;
-        // own block: all non-Repeat tables (Repeat ones return 0 bytes and are not wanted)
-        st = zk_locate_seq_tables(sm, b, blk.size, want, &bits_off);
-        sm.bits_off = bits_off;
-        const int32_t refs[3] = { blk.ll_ref, blk.of_ref, blk.ml_ref };
-        for (int t = 0; t < 3 && !st; t++) {
-            if (refs[t] < 0) continue;
-            const ZkBlock& rb = a.blocks[refs[t]];
-            bool w2[3] = { t == 0, t == 1, t == 2 };
-            uint32_t dummy;
-            st = zk_locate_seq_tables(sm, ebase + rb.src, rb.size, w2, &dummy);
-        }
-        sm.st_seq = st;
-    }
-    __syncwarp();
-    if (sm.st_seq) return;
-    int bst = 0;
-    if (lane < 3) bst = zk_build_seq_table(sm, lane);
-    uint32_t bad = __ballot_sync(0xFFFFFFFFu, bst != 0);
-    if (bad) { if (lane == 0) sm.st_seq = ZKZ_CORRUPTION; return; }
-    __syncwarp();
-    if (lane != 0) return;
-
-    // ---- serial FSE decode of the interleaved LL/OF/ML states (A.5)
-    ZkBackBits br;
-    uint32_t bits_off = sm.bits_off;
-    if (!br.init(b + bits_off, blk.size - bits_off)) { sm.st_seq = ZKZ_CORRUPTION; return; }
-    const int ll_log = sm.tbl_log[0], of_log = sm.tbl_log[1], ml_log = sm.tbl_log[2];
-    br.refill();
-    uint32_t sl = br.read(ll_log), so = br.read(of_log), smm = br.read(ml_log);
-    uint32_t r0 = ZK_SYM_MAKE(0, 0), r1 = ZK_SYM_MAKE(1, 0), r2 = ZK_SYM_MAKE(2, 0);
-    uint32_t lit_end = 0, out_end = 0;
-    uint32_t* o_lit = a.seq_lit_end + blk.seq_base;
-    uint32_t* o_out = a.seq_out_end + blk.seq_base;
-    uint32_t* o_off = a.seq_off + blk.seq_base;
-    const uint32_t nseq = blk.nseq;
-    int st = 0;
-    for (uint32_t i = 0; i < nseq; i++) {
-        ZkSeqCell cl = sm.ll[sl], co = sm.of[so], cm = sm.ml[smm];
-        br.refill();                                                  // <= 31 + 16 + 16 bits follow
-        uint32_t ofv = co.base_value + br.read(co.add_bits);
-        uint32_t mlv = cm.base_value + br.read(cm.add_bits);
-        uint32_t llv = cl.base_value + br.read(cl.add_bits);
-        br.refill();                                                  // <= 9 + 9 + 8 bits follow
-        if (i + 1 < nseq) {
-            sl = cl.next_base + br.read(cl.nb_bits);
-            smm = cm.next_base + br.read(cm.nb_bits);
-            so = co.next_base + br.read(co.nb_bits);
-        }
-        // repeat-offset history, kept symbolic w.r.t. the (unknown) state entering this block
-        uint32_t off;
-        if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
-        else {
-            uint32_t idx = ofv - 1 + (llv == 0);
-            if (idx == 0) off = r0;
-            else {
-                if (idx == 3) {
-                    if (r0 & ZK_SYM) off = r0 + 1;                    // delta + 1
-                    else { off = r0 - 1; if (off == 0) st = ZKZ_CORRUPTION; }
-                } else off = idx == 1 ? r1 : r2;
-                if (idx != 1) r2 = r1;
-                r1 = r0; r0 = off;
-            }
-        }
-        lit_end += llv; out_end += llv + mlv;
-        o_lit[i] = lit_end; o_out[i] = out_end; o_off[i] = off;
-    }
-    if (br.bp != 0) st = ZKZ_CORRUPTION;
-    if (lit_end > blk.lit_size) st = ZKZ_CORRUPTION;
-    else if (out_end + (blk.lit_size - lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
-    a.blocks[bidx].rep_out[0] = r0; a.blocks[bidx].rep_out[1] = r1; a.blocks[bidx].rep_out[2] = r2;
-    a.blocks[bidx].regen = out_end + (blk.lit_size - lit_end);
-    sm.st_seq = st;
-}
-
-__global__ void __launch_bounds__(ZK_D1_THREADS) zk_entropy_kernel(ZkDecodeArgs a) {
-    __shared__ ZkD1Smem sm;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
+    ZK_DYN_SMEM(smem);
+    ZkHufSlot* slots = (ZkHufSlot*)smem;
+    const int lane = threadIdx.x, si = lane >> 2, stream = lane & 3;
+    if (a.counters->overflow) return;
+    const uint32_t n = a.counters->n_huf_blocks;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sm.work = atomicAdd(a.work_counter, 1u);
-        __syncthreads();
-        uint32_t bidx = sm.work;
-        unsigned long long nb = a.counters->n_blocks;
-        if (a.counters->overflow) nb = 0;                   // scratch too small: the host grows it and re-runs the batch
-        if (bidx >= nb) break;
-        ZkBlock blk = a.blocks[bidx];
-        if (blk.type != 2) continue;                         // Raw / RLE: regen preset by the scan kernel
-        if (a.entries[blk.entry].status != 0) continue;
-        const uint8_t* ebase = a.comp + a.c_off[blk.entry];
-        if (threadIdx.x == 0) { sm.st_lit = 0; sm.st_seq = 0; }
-        __syncthreads();
-        if (warp == 0) zk_d1_sequences(sm, a, blk, bidx, ebase, lane);
-        else zk_d1_literals(sm, a, blk, bidx, ebase, lane);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int st = sm.st_lit ? sm.st_lit : sm.st_seq;
-            if (blk.nseq == 0) a.blocks[bidx].regen = blk.lit_size;
-            a.blocks[bidx].status = st ? -st : 0;
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&a.work_counter[1], 1u);
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        uint32_t first = g * ZK_HUF_SLOTS;
+        if (first >= n) break;
+        const uint32_t my = first + si;
+        const bool active = my < n;
+        ZkHufSlot& sl = slots[si];
+        uint32_t bidx = 0; ZkBlock blk; ZkLitHdr lh; const uint8_t* ebase = nullptr;
+        bool live = false;
+        if (active) {
+            bidx = a.huf_list[my];
+            blk = a.blocks[bidx];
+            live = a.entries[blk.entry].status == 0;
+            ebase = a.comp + a.c_off[blk.entry];
+            zk_parse_lit_hdr(ebase + blk.src, blk.size, lh);      // validated by the scan kernel
         }
+        // 1. tree description (own block, or the block a Treeless block refers to) -- one lane per block
+        if (live && stream == 0) {
+            int st = 0; uint32_t tb = 0;
+            if (lh.type == 2) { tb = zk_read_huf_weights(sl, ebase + blk.src + lh.hdr, lh.comp); if (!tb) st = ZKZ_CORRUPTION; }
+            else {
+                const ZkBlock& rb = a.blocks[blk.huf_ref];
+                ZkLitHdr rh; zk_parse_lit_hdr(ebase + rb.src, rb.size, rh);
+                if (!zk_read_huf_weights(sl, ebase + rb.src + rh.hdr, rh.comp)) st = ZKZ_CORRUPTION;
+            }
+            if (!st) {   // start cell of every symbol: weight ascending, symbols in natural order
+                uint32_t rank_start[13], cntw[13];
+                for (int w = 0; w < 13; w++) cntw[w] = 0;
+                for (int s = 0; s < sl.nw; s++) cntw[sl.weights[s]]++;
+                uint32_t acc = 0;
+                for (int w = 1; w <= sl.huf_bits; w++) { rank_start[w] = acc; acc += cntw[w] << (w - 1); }
+                for (int s = 0; s < sl.nw; s++) { int w = sl.weights[s]; if (w) { sl.hpos[s] = (uint16_t)rank_start[w]; rank_start[w] += 1u << (w - 1); } }
+                if (acc != (1u << sl.huf_bits)) st = ZKZ_CORRUPTION;
+            }
+            sl.st = st; sl.tree_bytes = tb;
+        }
+        __syncwarp();
+        // 2. fill the decoding table -- the block's four lanes share the symbols
+        const bool good = live && sl.st == 0;
+        if (good) {
+            const int max_bits = sl.huf_bits;
+            for (int s = stream; s < sl.nw; s += 4) {
+                int w = sl.weights[s];
+                if (!w) continue;
+                uint32_t len = 1u << (w - 1), pos = sl.hpos[s];
+                uint16_t e = (uint16_t)(((max_bits + 1 - w) << 8) | s);
+                for (uint32_t i = 0; i < len; i++) sl.tbl[pos + i] = e;
+            }
+        }
+        __syncwarp();
+        // 3. decode: one lane per stream
+        bool ok = true;
+        if (good) {
+            const uint8_t* q = ebase + blk.src + lh.hdr + sl.tree_bytes;
+            uint32_t qn = lh.comp - sl.tree_bytes;
+            uint8_t* out = a.lit + blk.lit_base;
+            if (lh.streams == 1) {
+                if (stream == 0) ok = zk_huf_decode_stream(sl.tbl, sl.huf_bits, q, qn, out, lh.regen);
+            } else {
+                uint32_t seg = (lh.regen + 3) / 4;
+                if (qn < 10 || lh.regen < 6 || seg * 3 > lh.regen) ok = false;   // jump table + 4 non-empty streams; libzstd rejects regen < 6
+                else {
+                    uint32_t s1 = zk_ld_le16(q), s2 = zk_ld_le16(q + 2), s3 = zk_ld_le16(q + 4);
+                    if (6 + s1 + s2 + s3 >= qn) ok = false;
+                    else {
+                        uint32_t s4 = qn - 6 - s1 - s2 - s3;
+                        uint32_t off = stream == 0 ? 0 : (stream == 1 ? s1 : (stream == 2 ? s1 + s2 : s1 + s2 + s3));
+                        uint32_t len = stream == 0 ? s1 : (stream == 1 ? s2 : (stream == 2 ? s3 : s4));
+                        uint32_t cnt = stream < 3 ? seg : lh.regen - 3 * seg;
+                        ok = zk_huf_decode_stream(sl.tbl, sl.huf_bits, q + 6 + off, len, out + stream * seg, cnt);
+                    }
+                }
+            }
+        }
+        uint32_t bad = __ballot_sync(0xFFFFFFFFu, !ok);
+        if (live && stream == 0) {
+            int st = sl.st;
+            if (!st && ((bad >> (si * 4)) & 0xFu)) st = ZKZ_CORRUPTION;
+            a.blocks[bidx].lit_status = st ? -st : 0;
+        }
+        __syncwarp();
     }
 }
 
 // =============================================================================================
-// K-D2: ordered sequence execution
+// K-D2: ordered sequence execution with a shared-memory window.
+//
+// One CTA per seek-table entry, W warps.  The entry's sequences are cut into chunks of 32 (one per
+// lane); chunk c belongs to warp c % W.  The last R bytes of output live in a shared-memory ring:
+// every copy writes into the ring, dependent (recent) match sources are read from the ring
+// (~30-cycle latency instead of an L2 round trip -- the first version spent 60 % of its samples
+// waiting on those), and each finished chunk is flushed to HBM with 16-byte stores.
+//   * done_pos / done_chunk : in-order publication of finished chunks (everything below done_pos
+//     is final AND flushed to HBM);
+//   * a chunk may start once its end lies within R/2 of done_pos, so the in-flight region never
+//     laps the ring; a source at distance < R/2 from the chunk start is therefore still resident;
+//   * chunks larger than R/2, Raw/RLE blocks and literal-only blocks run alone ("direct" path:
+//     HBM to HBM, then the ring is re-synchronised from HBM).
 // =============================================================================================
-// warp-cooperative copy of n bytes, non-overlapping (or src entirely before dst with distance >= n)
+#define ZK_LONG 48u     // literal runs / matches at least this long are copied by the whole warp
+
+struct ZkD2Smem {
+    volatile uint32_t done_pos;      // every output byte below this position (entry-relative) is final and in HBM
+    volatile uint32_t done_chunk;    // chunks [0, done_chunk) are published
+    volatile int abort_code;
+};
+
+__device__ __forceinline__ void zk_d2_abort(ZkD2Smem& sm, int code) { atomicCAS((int*)&sm.abort_code, 0, code); }
+// warp-uniform view of the abort flag (every lane must take the same branch around collectives)
+__device__ __forceinline__ bool zk_d2_aborted(ZkD2Smem& sm) { return __any_sync(0xFFFFFFFFu, sm.abort_code != 0); }
+
+// warp-cooperative copy of n bytes HBM -> HBM, non-overlapping (or src entirely before dst with distance >= n)
 __device__ __forceinline__ void zk_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
     uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
@@ -620,7 +654,7 @@ __device__ __forceinline__ void zk_warp_fill(uint8_t* dst, uint32_t byte, uint32
     for (uint32_t i = (nvec << 4) + lane; i < n; i += 32) dst[i] = (uint8_t)byte;
 }
 
-// warp-cooperative match copy dst[0..n) = dst[-off ..), overlap allowed (period doubling)
+// warp-cooperative match copy in HBM: dst[0..n) = dst[-off ..), overlap allowed (period doubling)
 __device__ __forceinline__ void zk_warp_match(uint8_t* dst, uint32_t off, uint32_t n, int lane) {
     const uint8_t* src = dst - off;
     if (off >= n) { zk_warp_copy(dst, src, n, lane); return; }
@@ -633,17 +667,36 @@ __device__ __forceinline__ void zk_warp_match(uint8_t* dst, uint32_t off, uint32
     }
 }
 
-#define ZK_LONG 48u     // sequences whose literal run / match is at least this long are copied by the whole warp
-
-struct ZkD2Smem {
-    volatile uint32_t done_pos;      // every output byte below this position (entry-relative) is final
-    volatile uint32_t done_chunk;    // chunks [0, done_chunk) are published
-    volatile int abort_code;
+// per-CTA view of the ring: position p (entry-relative) lives at ring[(p + mis) & mask], mis = (out address & 15)
+// so that 16-byte groups of the ring line up with 16-byte groups of HBM.
+struct ZkRing {
+    uint8_t* ring; uint32_t mask, mis; uint8_t* out;
+    __device__ __forceinline__ uint8_t& at(uint32_t p) const { return ring[(p + mis) & mask]; }
 };
 
-__device__ __forceinline__ void zk_d2_abort(ZkD2Smem& sm, int code) { atomicCAS((int*)&sm.abort_code, 0, code); }
-// warp-uniform view of the abort flag (every lane must take the same branch around collectives)
-__device__ __forceinline__ bool zk_d2_aborted(ZkD2Smem& sm) { return __any_sync(0xFFFFFFFFu, sm.abort_code != 0); }
+// flush [s, e) ring -> HBM: full 16-byte groups with vector stores, ragged ends bytewise (neighbours own the rest)
+__device__ __forceinline__ void zk_ring_flush(const ZkRing& rg, uint32_t s, uint32_t e, int lane) {
+    if (e <= s) return;
+    const uint32_t u0 = (s + rg.mis) >> 4, u1 = (e + rg.mis - 1) >> 4;     // 16-byte groups touched
+    for (uint32_t u = u0 + lane; u <= u1; u += 32) {
+        const uint32_t g = u << 4;                                        // shifted position of the group
+        const uint32_t lo = g > s + rg.mis ? g : s + rg.mis, hi = g + 16 < e + rg.mis ? g + 16 : e + rg.mis;
+        if (hi - lo == 16) *(uint4*)(rg.out + (g - rg.mis)) = *(const uint4*)(rg.ring + (g & rg.mask));
+        else for (uint32_t q = lo; q < hi; q++) rg.out[q - rg.mis] = rg.ring[q & rg.mask];
+    }
+}
+
+// reload [s, e) HBM -> ring (after a direct HBM-to-HBM block)
+__device__ __forceinline__ void zk_ring_reload(const ZkRing& rg, uint32_t s, uint32_t e, int tid, int nthr) {
+    if (e <= s) return;
+    const uint32_t u0 = (s + rg.mis) >> 4, u1 = (e + rg.mis - 1) >> 4;
+    for (uint32_t u = u0 + tid; u <= u1; u += nthr) {
+        const uint32_t g = u << 4;
+        const uint32_t lo = g > s + rg.mis ? g : s + rg.mis, hi = g + 16 < e + rg.mis ? g + 16 : e + rg.mis;
+        if (hi - lo == 16) *(uint4*)(rg.ring + (g & rg.mask)) = *(const uint4*)(rg.out + (g - rg.mis));
+        else for (uint32_t q = lo; q < hi; q++) rg.ring[q & rg.mask] = rg.out[q - rg.mis];
+    }
+}
 
 // wait until it is chunk c's turn, then publish its end position
 __device__ __forceinline__ void zk_d2_publish(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, int lane) {
@@ -658,8 +711,28 @@ __device__ __forceinline__ void zk_d2_publish(ZkD2Smem& sm, uint32_t c, uint32_t
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
+// warp-uniform wait: returns false if the CTA aborted.  Waits until chunk c may start:
+// exclusive == false: its end lies within `window` of done_pos;  exclusive == true: it is the oldest chunk.
+__device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, uint32_t window, bool exclusive, int lane) {
+    for (;;) {
+        uint32_t ok = 0, ab = 0;
+        if (lane == 0) {
+            ab = sm.abort_code != 0;
+            uint32_t dc = sm.done_chunk, dp = sm.done_pos;
+            ok = exclusive ? (dc == c) : (dc == c || end_pos - dp <= window);
+            __threadfence_block();
+        }
+        ok = __shfl_sync(0xFFFFFFFFu, ok, 0); ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
+        __syncwarp();
+        if (ab) return false;
+        if (ok) return true;
+        ZK_SPIN();
+    }
+}
+
+__global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t ring_bytes) {
     __shared__ ZkD2Smem sm;
+    ZK_DYN_SMEM(ring_mem);
     const uint32_t e = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     ZkEntry ent = a.entries[e];
@@ -670,6 +743,8 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
     const unsigned long long cap64 = a.d_off[e + 1] - a.d_off[e];
     const uint32_t cap = cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cap64;
     const uint8_t* ebase = a.comp + a.c_off[e];
+    ZkRing rg; rg.ring = ring_mem; rg.mask = ring_bytes - 1; rg.mis = (uint32_t)((uintptr_t)out & 15); rg.out = out;
+    const uint32_t half = ring_bytes >> 1;
 
     uint32_t pos = 0, zstart = 0, chunk_base = 0;
     uint32_t R0 = 1, R1 = 4, R2 = 8;
@@ -678,21 +753,23 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
         const uint32_t bidx = ent.first_block + bi;
         const ZkBlock blk = a.blocks[bidx];
         if (blk.flags & ZKB_FIRST) { R0 = 1; R1 = 4; R2 = 8; zstart = pos; }
-        if (blk.status != 0) { zk_d2_abort(sm, -blk.status); break; }
+        if (blk.status != 0 || blk.lit_status != 0) { zk_d2_abort(sm, blk.status ? -blk.status : -blk.lit_status); break; }
         const bool has_seq = blk.type == 2 && blk.nseq > 0;
         const uint32_t nchunks = has_seq ? (blk.nseq + 31) / 32 + 1 : 1;
         if ((unsigned long long)pos + blk.regen > cap) { zk_d2_abort(sm, ZKZ_DST_TOO_SMALL); break; }
         // first chunk index of this block that belongs to this warp
         uint32_t c = chunk_base + ((uint32_t)warp + W - (chunk_base % W)) % W;
         for (; c < chunk_base + nchunks; c += W) {
-            if (zk_d2_aborted(sm)) break;
             const uint32_t j = c - chunk_base;
             if (!has_seq) {
-                // ---------------- Raw block / RLE block / literals-only compressed block
+                // ---------------- Raw block / RLE block / literals-only compressed block: direct path, runs alone
+                if (!zk_d2_wait_start(sm, c, 0, 0, true, lane)) break;
                 if (blk.type == 0) zk_warp_copy(out + pos, ebase + blk.src, blk.size, lane);
                 else if (blk.type == 1) zk_warp_fill(out + pos, ebase[blk.src], blk.size, lane);
                 else if (blk.lit_kind == 1) zk_warp_fill(out + pos, blk.lit_byte, blk.lit_size, lane);
                 else zk_warp_copy(out + pos, blk.lit_kind == 0 ? ebase + blk.lit_src : a.lit + blk.lit_base, blk.lit_size, lane);
+                __syncwarp();
+                { uint32_t en = pos + blk.regen; zk_ring_reload(rg, en > half ? en - half : 0, en, lane, 32); }
                 zk_d2_publish(sm, c, pos + blk.regen, lane);
                 continue;
             }
@@ -701,11 +778,21 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
             const uint8_t* lit = blk.lit_kind == 0 ? ebase + blk.lit_src : a.lit + blk.lit_base;
             if (j == nchunks - 1) {
                 // ---------------- trailing literals of the block
-                uint32_t le = s_lit[blk.nseq - 1], oe = s_out[blk.nseq - 1];
-                uint32_t n = blk.lit_size - le;
-                if (blk.lit_kind == 1) zk_warp_fill(out + pos + oe, blk.lit_byte, n, lane);
-                else zk_warp_copy(out + pos + oe, lit + le, n, lane);
-                zk_d2_publish(sm, c, pos + blk.regen, lane);
+                const uint32_t le = s_lit[blk.nseq - 1], oe = s_out[blk.nseq - 1];
+                const uint32_t n = blk.lit_size - le, st0 = pos + oe, en = pos + blk.regen;
+                const bool direct = n > half;
+                if (!zk_d2_wait_start(sm, c, en, half, direct, lane)) break;
+                if (direct) {
+                    if (blk.lit_kind == 1) zk_warp_fill(out + st0, blk.lit_byte, n, lane);
+                    else zk_warp_copy(out + st0, lit + le, n, lane);
+                    __syncwarp();
+                    zk_ring_reload(rg, en - half, en, lane, 32);
+                } else {
+                    for (uint32_t i = lane; i < n; i += 32) rg.at(st0 + i) = blk.lit_kind == 1 ? blk.lit_byte : lit[le + i];
+                    __syncwarp();
+                    zk_ring_flush(rg, st0, en, lane);
+                }
+                zk_d2_publish(sm, c, en, lane);
                 continue;
             }
             // ---------------- 32 sequences, one per lane
@@ -728,25 +815,71 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
                 if (off == 0 || off > md - zstart) bad = true;
             }
             if (__any_sync(0xFFFFFFFFu, bad)) { zk_d2_abort(sm, ZKZ_CORRUPTION); break; }
+            const uint32_t chunk_start = pos + __shfl_sync(0xFFFFFFFFu, oe_prev, 0);
             const uint32_t chunk_end = pos + __shfl_sync(0xFFFFFFFFu, oe, min(31u, blk.nseq - 1 - j * 32));
+            const bool direct = chunk_end - chunk_start > half;
+            if (!zk_d2_wait_start(sm, c, chunk_end, half, direct, lane)) break;
 
-            // literal runs: no dependencies
+            if (direct) {
+                // ======== huge chunk: HBM -> HBM, alone in flight (it is the oldest chunk)
+                if (valid && ll < ZK_LONG) {
+                    uint8_t* d = out + o_lit;
+                    if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) d[i] = blk.lit_byte;
+                    else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) d[i] = sp[i]; }
+                }
+                uint32_t longlit = __ballot_sync(0xFFFFFFFFu, valid && ll >= ZK_LONG);
+                while (longlit) {
+                    int l = __ffs((int)longlit) - 1; longlit &= longlit - 1;
+                    uint32_t n = __shfl_sync(0xFFFFFFFFu, ll, l), d = __shfl_sync(0xFFFFFFFFu, o_lit, l), sp = __shfl_sync(0xFFFFFFFFu, le_prev, l);
+                    if (blk.lit_kind == 1) zk_warp_fill(out + d, blk.lit_byte, n, lane);
+                    else zk_warp_copy(out + d, lit + sp, n, lane);
+                }
+                __syncwarp();
+                const uint32_t need_end = md - off + (ml < off ? ml : off);
+                uint32_t pending = __ballot_sync(0xFFFFFFFFu, valid && ml > 0);
+                while (pending) {
+                    const int first = __ffs((int)pending) - 1;
+                    const uint32_t frontier = __shfl_sync(0xFFFFFFFFu, md, first);
+                    const bool mine = (pending >> lane) & 1;
+                    const bool ready = mine && (need_end <= frontier || lane == first);
+                    const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, ready);
+                    if (ready && ml < ZK_LONG) {
+                        uint8_t* d = out + md; const uint8_t* sp = d - off;
+                        for (uint32_t i = 0; i < ml; i++) d[i] = sp[i];
+                    }
+                    uint32_t longm = __ballot_sync(0xFFFFFFFFu, ready && ml >= ZK_LONG);
+                    while (longm) {
+                        int l = __ffs((int)longm) - 1; longm &= longm - 1;
+                        uint32_t n = __shfl_sync(0xFFFFFFFFu, ml, l), d = __shfl_sync(0xFFFFFFFFu, md, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
+                        zk_warp_match(out + d, o, n, lane);
+                    }
+                    __syncwarp();
+                    pending &= ~rmask;
+                }
+                zk_ring_reload(rg, chunk_end - half, chunk_end, lane, 32);
+                zk_d2_publish(sm, c, chunk_end, lane);
+                continue;
+            }
+
+            // ======== normal chunk: build the output in the ring, then flush
+            // literal runs: no dependencies (HBM scratch -> ring)
             if (valid && ll < ZK_LONG) {
-                uint8_t* d = out + o_lit;
-                if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) d[i] = blk.lit_byte;
-                else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) d[i] = sp[i]; }
+                if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) rg.at(o_lit + i) = blk.lit_byte;
+                else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) rg.at(o_lit + i) = sp[i]; }
             }
             uint32_t longlit = __ballot_sync(0xFFFFFFFFu, valid && ll >= ZK_LONG);
             while (longlit) {
                 int l = __ffs((int)longlit) - 1; longlit &= longlit - 1;
                 uint32_t n = __shfl_sync(0xFFFFFFFFu, ll, l), d = __shfl_sync(0xFFFFFFFFu, o_lit, l), sp = __shfl_sync(0xFFFFFFFFu, le_prev, l);
-                if (blk.lit_kind == 1) zk_warp_fill(out + d, blk.lit_byte, n, lane);
-                else zk_warp_copy(out + d, lit + sp, n, lane);
+                for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = blk.lit_kind == 1 ? blk.lit_byte : lit[sp + i];
             }
             __syncwarp();
 
-            // matches: a lane may go once every byte of its source is final
-            const uint32_t need_end = md - off + (ml < off ? ml : off);
+            // matches.  near: the whole source is still resident in the ring (distance < R/2 from the chunk start);
+            // far: it is read from HBM and must be published (done_pos).  A lane may go once its source is final.
+            const uint32_t src0 = md - off;
+            const bool near_src = src0 + half >= chunk_start;          // src0 >= chunk_start - R/2
+            const uint32_t need_end = src0 + (ml < off ? ml : off);
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, valid && ml > 0);
             bool aborted = false;
             while (pending) {
@@ -754,6 +887,7 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
                 uint32_t dc = 0, dp = 0, ab = 0;
                 if (lane == 0) { dc = sm.done_chunk; dp = sm.done_pos; ab = sm.abort_code != 0; __threadfence_block(); }
                 dc = __shfl_sync(0xFFFFFFFFu, dc, 0); dp = __shfl_sync(0xFFFFFFFFu, dp, 0); ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
+                __syncwarp();                      // orders the other lanes' data reads after lane 0's acquire
                 if (ab) { aborted = true; break; }
                 const bool oldest = dc == c;
                 const int first = __ffs((int)pending) - 1;
@@ -764,19 +898,27 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a) {
                 const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, ready);
                 if (!rmask) { ZK_SPIN(); continue; }
                 if (ready && ml < ZK_LONG) {
-                    uint8_t* d = out + md; const uint8_t* sp = d - off;
-                    for (uint32_t i = 0; i < ml; i++) d[i] = sp[i];
+                    if (near_src) for (uint32_t i = 0; i < ml; i++) rg.at(md + i) = rg.at(src0 + i);
+                    else { const uint8_t* sp = out + src0; for (uint32_t i = 0; i < ml; i++) rg.at(md + i) = sp[i]; }
                 }
                 uint32_t longm = __ballot_sync(0xFFFFFFFFu, ready && ml >= ZK_LONG);
                 while (longm) {
                     int l = __ffs((int)longm) - 1; longm &= longm - 1;
-                    uint32_t n = __shfl_sync(0xFFFFFFFFu, ml, l), d = __shfl_sync(0xFFFFFFFFu, md, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
-                    zk_warp_match(out + d, o, n, lane);
+                    const uint32_t n = __shfl_sync(0xFFFFFFFFu, ml, l), d = __shfl_sync(0xFFFFFFFFu, md, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
+                    const bool nr = __shfl_sync(0xFFFFFFFFu, (uint32_t)near_src, l) != 0;
+                    if (!nr) { const uint8_t* sp = out + (d - o); for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = sp[i]; }
+                    else if (o >= n) { for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = rg.at(d - o + i); }
+                    else if (o >= 32) {           // overlapping, period >= 32: 32 bytes per step are already final
+                        for (uint32_t i0 = 0; i0 < n; i0 += 32) { uint32_t i = i0 + lane; if (i < n) rg.at(d + i) = rg.at(d - o + i); __syncwarp(); }
+                    } else {                      // short period: replicate the pattern
+                        for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = rg.at(d - o + (i % o));
+                    }
                 }
                 __syncwarp();
                 pending &= ~rmask;
             }
             if (aborted) break;
+            zk_ring_flush(rg, chunk_start, chunk_end, lane);
             zk_d2_publish(sm, c, chunk_end, lane);
         }
         // advance to the next block
@@ -898,7 +1040,8 @@ static int zk_grow(void** p, size_t* cap, size_t need, size_t elem) {
 }
 
 void zk_decode_ws_free(ZkDecodeWs* ws) {
-    void* ptrs[] = { ws->blocks, ws->entries, ws->counters, ws->lit, ws->seq_lit_end, ws->seq_out_end, ws->seq_off, ws->c_off, ws->d_off };
+    void* ptrs[] = { ws->blocks, ws->entries, ws->counters, ws->lit, ws->seq_lit_end, ws->seq_out_end, ws->seq_off, ws->c_off, ws->d_off,
+                     ws->huf_list, ws->seq_list };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ws->h_entries) cudaFreeHost(ws->h_entries);
     if (ws->h_counters) cudaFreeHost(ws->h_counters);
@@ -909,7 +1052,13 @@ void zk_decode_ws_free(ZkDecodeWs* ws) {
 static int zk_decode_ensure(ZkDecodeWs* ws, uint32_t n, size_t need_blocks, size_t need_lit, size_t need_seq) {
     int rc;
     size_t cap;
-    cap = ws->cap_blocks; if ((rc = zk_grow((void**)&ws->blocks, &cap, need_blocks, sizeof(ZkBlock)))) return rc; ws->cap_blocks = cap;
+    if (ws->cap_blocks < need_blocks || !ws->blocks) {
+        size_t c1 = ws->cap_blocks, c2 = ws->cap_blocks, c3 = ws->cap_blocks;
+        if ((rc = zk_grow((void**)&ws->blocks, &c1, need_blocks, sizeof(ZkBlock)))) return rc;
+        if ((rc = zk_grow((void**)&ws->huf_list, &c2, need_blocks, 4))) return rc;
+        if ((rc = zk_grow((void**)&ws->seq_list, &c3, need_blocks, 4))) return rc;
+        ws->cap_blocks = c1 < c2 ? (c1 < c3 ? c1 : c3) : (c2 < c3 ? c2 : c3);
+    }
     cap = ws->cap_lit; if ((rc = zk_grow((void**)&ws->lit, &cap, need_lit + 64, 1))) return rc; ws->cap_lit = cap;
     if (ws->cap_seq < need_seq || !ws->seq_off) {
         size_t c1 = ws->cap_seq, c2 = ws->cap_seq, c3 = ws->cap_seq;
@@ -963,22 +1112,38 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     ZkDecodeArgs a;
     a.comp = d_comp; a.c_off = (const unsigned long long*)ws->c_off; a.d_off = (const unsigned long long*)ws->d_off; a.dst = d_dst; a.n_entries = n;
     a.blocks = ws->blocks; a.entries = ws->entries; a.counters = ws->counters;
-    a.work_counter = (uint32_t*)((uint8_t*)ws->counters + sizeof(ZkCounters));
+    a.work_counter = (uint32_t*)((uint8_t*)ws->counters + sizeof(ZkCounters));   // two counters (seq, huf), zeroed with the struct
     a.lit = ws->lit; a.seq_lit_end = ws->seq_lit_end; a.seq_out_end = ws->seq_out_end; a.seq_off = ws->seq_off;
+    a.huf_list = ws->huf_list; a.seq_list = ws->seq_list;
     a.cap_blocks = ws->cap_blocks; a.cap_lit = ws->cap_lit - 64; a.cap_seq = ws->cap_seq;
     ZK_LAUNCH(zk_scan_kernel, (n + 127) / 128, 128, 0, stream, a);
-    uint32_t g1 = (uint32_t)sms * 16;
+    // entropy stage: persistent warp-CTAs pulling groups of blocks from a work counter
     size_t est_blocks = (size_t)(total_d / ZK_BLOCK_MAX) + n;
-    if (est_blocks < g1) g1 = (uint32_t)(est_blocks < 1 ? 1 : est_blocks);
-    ZK_LAUNCH(zk_entropy_kernel, g1, ZK_D1_THREADS, 0, stream, a);
+    const size_t seq_smem = sizeof(ZkSeqSlot) * ZK_SEQ_LANES, huf_smem = sizeof(ZkHufSlot) * ZK_HUF_SLOTS;
+    if (!ws->attr_set) {
+        ZK_CUDA_OK(cudaFuncSetAttribute(zk_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
+        ZK_CUDA_OK(cudaFuncSetAttribute(zk_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem));
+        ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        ws->attr_set = true;
+    }
+    uint32_t gs = (uint32_t)sms * 2, gh = (uint32_t)sms * 5;
+    size_t need_s = est_blocks / ZK_SEQ_LANES + 1, need_h = est_blocks / ZK_HUF_SLOTS + 1;
+    if (need_s < gs) gs = (uint32_t)need_s;
+    if (need_h < gh) gh = (uint32_t)need_h;
+    ZK_LAUNCH(zk_seq_kernel, gs, 32, seq_smem, stream, a);
+    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem, stream, a);
+    // exec stage: ring size / warps per entry chosen from how many entries share the machine
     int W = exec_warps;
-    if (W <= 0) { long per = ((long)sms * 48) / (long)n; W = per < 4 ? 4 : (per > 16 ? 16 : (int)per); }
+    uint32_t ring = 32 * 1024;
+    if (W <= 0) { long per = ((long)sms * 32) / (long)n; W = per < 4 ? 4 : (per > 16 ? 16 : (int)per); }
     if (W > 16) W = 16;
-    ZK_LAUNCH(zk_exec_kernel, n, W * 32, 0, stream, a);
+    if ((long)n * 2 <= sms) ring = 128 * 1024; else if ((long)n * 3 <= (long)sms * 2) ring = 64 * 1024;
+    if (ws->ring_override) ring = ws->ring_override;
+    ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
     if (verify_checksum) ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a);
     ZK_CUDA_OK(cudaMemcpyAsync(ws->h_entries, ws->entries, (size_t)n * sizeof(ZkEntry), cudaMemcpyDeviceToHost, stream));
     ZK_CUDA_OK(cudaMemcpyAsync(ws->h_counters, ws->counters, sizeof(ZkCounters), cudaMemcpyDeviceToHost, stream));
-    ws->launches += 3 + (verify_checksum ? 1 : 0);
+    ws->launches += 4 + (verify_checksum ? 1 : 0);
     ws->pending_n = n;
     return 0;
 }

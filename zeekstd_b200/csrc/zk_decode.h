@@ -11,6 +11,7 @@ struct ZkDecodeArgs {                 // kernel parameter block (by value)
     uint32_t n_entries;
     ZkBlock* blocks; ZkEntry* entries; ZkCounters* counters; uint32_t* work_counter;
     uint8_t* lit; uint32_t* seq_lit_end; uint32_t* seq_out_end; uint32_t* seq_off;
+    uint32_t* huf_list; uint32_t* seq_list;   // compacted indices of blocks with Huffman literals / with sequences
     unsigned long long cap_blocks, cap_lit, cap_seq;
 };
 
@@ -21,6 +22,8 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint8_t* lit = nullptr; size_t cap_lit = 0;
     uint32_t* seq_lit_end = nullptr; uint32_t* seq_out_end = nullptr; uint32_t* seq_off = nullptr; size_t cap_seq = 0;
     uint64_t* c_off = nullptr; uint64_t* d_off = nullptr;
+    uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
+    bool attr_set = false; uint32_t ring_override = 0;
     ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
     size_t want_blocks = 0, want_lit = 0, want_seq = 0;   // exact needs reported by a batch that overflowed
     uint32_t pending_n = 0;
