@@ -41,6 +41,11 @@ for kind in ["text", "structured", "lowent", "random", "runs"]:
 mix = corpus.make_mix(sz, device="cuda").cpu().numpy()
 out.append(run("mix-2M-L1", mix, 2 << 20, 1, False))
 out.append(run("mix-2M-L3ck", mix, 2 << 20, 3, True))
+if os.environ.get("ZK_CHECK_BIG"):
+    big = corpus.make_mix(1 << 30, device="cuda").cpu().numpy()
+    out.append(run("mix-1GiB-2M-L1", big, 2 << 20, 1, False, reps=3))
+    out.append(run("mix-1GiB-512K-L1", big, 512 << 10, 1, False, reps=3))
+    del big
 txt = corpus.make_text(sz, device="cuda").cpu().numpy()
 out.append(run("text-2M-L1", txt, 2 << 20, 1, False))
 out.append(run("text-512K-L1", txt, 512 << 10, 1, False))

@@ -15,7 +15,7 @@
 #include <cuda_runtime.h>
 #define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ZK_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
-#define ZK_SPIN() __nanosleep(20)
+#define ZK_SPIN() __nanosleep(64)
 #endif
 
 #include <stdint.h>
@@ -108,27 +108,38 @@ __device__ __forceinline__ uint32_t zk_ld_le32(const uint8_t* p) {
 __device__ __forceinline__ int zk_highbit(uint32_t v) { return 31 - __clz((int)v); }   // v != 0
 
 // -------------------------------------------------------------------------------------------
-// Backward bitstream reader (A.7) over global memory with a 128-bit register window.
+// Backward bitstream reader (A.7) over global memory.
 //
-// Coordinates: bit i of the stream lives at absolute bit (i + shift) of the 8-byte aligned word
-// array starting at a0 = stream address rounded down to 8.  The window holds the two aligned
-// 64-bit words [wbase/64, wbase/64+1]; one more word is prefetched so a refill never waits
-// on memory.  Reads below the start of the stream return zero bits (legal only at the very
-// end of Huffman-weight / Huffman-literal streams, A.4) and make `bp` negative, which callers
-// test for to detect corruption.
+// The stream is consumed from its last byte towards its first; `buf` holds the next unread bits
+// left-aligned (MSB = the bit just below the cursor), so reading n bits is one shift.  Memory is
+// fetched as aligned 32-bit words in descending order, always one word ahead (`nxt`), and the
+// cache line after that is prefetched, so a refill never waits for DRAM even though every lane of
+// a warp streams through a different region.  Reads below the first byte return zero bits (legal
+// only at the very end of Huffman streams / FSE-compressed weights, A.4) and drive `left` negative,
+// which callers test to detect corruption.
 // -------------------------------------------------------------------------------------------
-struct ZkBackBits {
-    const unsigned long long* a0;   // aligned base
-    unsigned long long hi, lo, nxt; // window words: hi = word(k+1), lo = word(k), nxt = word(k-1)
-    int k;                          // index of `lo`
-    int shift;                      // stream bit 0 = absolute bit `shift`
-    int bp;                         // cursor: number of unread stream bits (may go negative)
-    unsigned long long lowmask;     // mask clearing the bits below the stream start in word 0
+__device__ __forceinline__ void zk_prefetch_l1(const void* p) {
+#ifndef ZK_EMUL
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
 
-    __device__ __forceinline__ unsigned long long word(int idx) const {
-        if (idx < 0) return 0ull;
-        unsigned long long w = a0[idx];
-        return idx == 0 ? (w & lowmask) : w;
+struct ZkBackBits {
+    const uint32_t* w;          // 4-byte aligned base (stream address rounded down)
+    unsigned long long buf;     // unread bits, left-aligned
+    uint32_t nxt;               // prefetched word w[j]
+    uint32_t lowmask;           // clears the bits of word 0 that precede the stream
+    int j;                      // index of `nxt`
+    int cnt;                    // valid bits in buf
+    int bp;                     // stream bits not yet consumed (negative after an over-read)
+
+    // The word fetched ahead is kept RAW in `nxt` and only masked when it is merged into buf, so the load
+    // has a whole refill interval to complete (masking at load time made every refill wait for memory).
+    __device__ __forceinline__ uint32_t fetch(int idx) const { return w[idx < 0 ? 0 : idx]; }
+    __device__ __forceinline__ uint32_t cooked(uint32_t raw, int idx) const {
+        return idx < 0 ? 0u : (idx == 0 ? (raw & lowmask) : raw);
     }
     // returns false when the stream is malformed (empty or no end marker)
     __device__ __forceinline__ bool init(const uint8_t* p, uint32_t n) {
@@ -136,30 +147,31 @@ struct ZkBackBits {
         uint32_t last = p[n - 1];
         if (last == 0) return false;
         uintptr_t addr = (uintptr_t)p;
-        a0 = (const unsigned long long*)(addr & ~(uintptr_t)7);
-        shift = (int)(addr & 7) * 8;
-        lowmask = ~0ull << shift;
+        w = (const uint32_t*)(addr & ~(uintptr_t)3);
+        int shift = (int)(addr & 3) * 8;
+        lowmask = 0xFFFFFFFFu << shift;
         bp = (int)(n - 1) * 8 + zk_highbit(last);
-        // window must contain [cursor-64, cursor): place hi = word containing absolute bit (bp+shift-1)... or above
-        int top = (bp + shift + 63) >> 6;       // number of words needed to cover the cursor
-        k = top - 2;
-        hi = word(k + 1); lo = word(k); nxt = word(k - 1);
+        int A = bp + shift;                         // bits between the aligned base and the cursor
+        if (A == 0) { buf = 0; cnt = 0; j = -1; nxt = 0; return true; }
+        int t = (A - 1) >> 5, r = A - (t << 5);     // top word and how many of its low bits are payload
+        buf = (unsigned long long)cooked(fetch(t), t) << (64 - r);
+        cnt = r; j = t - 1; nxt = fetch(j);
+        if (j >= 32) zk_prefetch_l1(w + j - 32);
         return true;
     }
-    // make sure at least 64 bits below the cursor are inside the window
+    // afterwards at least 33 bits are available in buf (zero bits once the stream is exhausted)
     __device__ __forceinline__ void refill() {
-        int rel = bp + shift - k * 64;          // cursor position inside the window, (0,128]
-        if (rel < 64) { hi = lo; lo = nxt; k--; nxt = word(k - 1); }
+        if (cnt <= 32) {
+            buf |= (unsigned long long)cooked(nxt, j) << (32 - cnt);
+            cnt += 32; j--;
+            nxt = fetch(j);
+            if ((j & 31) == 31 && j >= 32) zk_prefetch_l1(w + j - 32);     // one line ahead of the word just fetched
+        }
     }
-    // n in [0,32]; the n bits just below the cursor, cursor unchanged.  Requires refill() since the last 64 consumed bits.
-    __device__ __forceinline__ uint32_t peek(int n) const {
-        int o = bp + shift - k * 64 - n;         // bit offset of the field inside the window, >= 32 after refill()
-        unsigned long long v;
-        if (o >= 64) v = hi >> (o - 64);
-        else v = (lo >> o) | ((hi << 1) << (63 - o));
-        return (uint32_t)v & (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
-    }
-    __device__ __forceinline__ uint32_t read(int n) { uint32_t v = peek(n); bp -= n; return v; }
+    // n in [0,32], n <= cnt
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)((buf >> 1) >> (63 - n)); }
+    __device__ __forceinline__ void skip(int n) { buf <<= n; cnt -= n; bp -= n; }
+    __device__ __forceinline__ uint32_t read(int n) { uint32_t v = peek(n); skip(n); return v; }
 };
 
 // Forward little-endian bit reader for FSE table descriptions (A.6); byte-wise, bounds checked.

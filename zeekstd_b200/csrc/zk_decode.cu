@@ -334,8 +334,9 @@ __device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkDecodeArgs& a, c
     const uint32_t nseq = blk.nseq;
     for (uint32_t i = 0; i < nseq; i++) {
         ZkSeqCell cl = sl.ll[s_l], co = sl.of[s_o], cm = sl.ml[s_m];
-        br.refill();                                                  // <= 31 + 16 + 16 bits follow
+        br.refill();                                                  // <= 31 bits follow
         uint32_t ofv = co.base_value + br.read(co.add_bits);
+        br.refill();                                                  // <= 16 + 16 bits follow
         uint32_t mlv = cm.base_value + br.read(cm.add_bits);
         uint32_t llv = cl.base_value + br.read(cl.add_bits);
         br.refill();                                                  // <= 9 + 9 + 8 bits follow
@@ -477,19 +478,20 @@ __device__ bool zk_huf_decode_stream(const uint16_t* tbl, int max_bits, const ui
     uint32_t i = 0;
     while (i < cnt && ((uintptr_t)(out + i) & 3)) {
         br.refill();
-        uint32_t e = tbl[br.peek(max_bits)]; br.bp -= (int)(e >> 8); out[i++] = (uint8_t)e;
+        uint32_t e = tbl[br.peek(max_bits)]; br.skip((int)(e >> 8)); out[i++] = (uint8_t)e;
     }
     for (; i + 4 <= cnt; i += 4) {
-        br.refill();                                   // 4 * 11 bits <= 64
-        uint32_t e0 = tbl[br.peek(max_bits)]; br.bp -= (int)(e0 >> 8);
-        uint32_t e1 = tbl[br.peek(max_bits)]; br.bp -= (int)(e1 >> 8);
-        uint32_t e2 = tbl[br.peek(max_bits)]; br.bp -= (int)(e2 >> 8);
-        uint32_t e3 = tbl[br.peek(max_bits)]; br.bp -= (int)(e3 >> 8);
+        br.refill();                                   // >= 33 bits: three codes of <= 11 bits
+        uint32_t e0 = tbl[br.peek(max_bits)]; br.skip((int)(e0 >> 8));
+        uint32_t e1 = tbl[br.peek(max_bits)]; br.skip((int)(e1 >> 8));
+        uint32_t e2 = tbl[br.peek(max_bits)]; br.skip((int)(e2 >> 8));
+        br.refill();
+        uint32_t e3 = tbl[br.peek(max_bits)]; br.skip((int)(e3 >> 8));
         *(uint32_t*)(out + i) = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | ((e3 & 0xFF) << 24);
     }
     for (; i < cnt; i++) {
         br.refill();
-        uint32_t e = tbl[br.peek(max_bits)]; br.bp -= (int)(e >> 8); out[i] = (uint8_t)e;
+        uint32_t e = tbl[br.peek(max_bits)]; br.skip((int)(e >> 8)); out[i] = (uint8_t)e;
     }
     return br.bp == 0;
 }
@@ -1046,6 +1048,9 @@ void zk_decode_ws_free(ZkDecodeWs* ws) {
     if (ws->h_entries) cudaFreeHost(ws->h_entries);
     if (ws->h_counters) cudaFreeHost(ws->h_counters);
     if (ws->h_off) cudaFreeHost(ws->h_off);
+    if (ws->side) cudaStreamDestroy(ws->side);
+    if (ws->ev_scan) cudaEventDestroy(ws->ev_scan);
+    if (ws->ev_huf) cudaEventDestroy(ws->ev_huf);
     *ws = ZkDecodeWs();
 }
 
@@ -1130,14 +1135,27 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     size_t need_s = est_blocks / ZK_SEQ_LANES + 1, need_h = est_blocks / ZK_HUF_SLOTS + 1;
     if (need_s < gs) gs = (uint32_t)need_s;
     if (need_h < gh) gh = (uint32_t)need_h;
+    // the two entropy kernels are independent: run the Huffman one on a side stream
+    if (!ws->side) {
+        ZK_CUDA_OK(cudaStreamCreateWithFlags(&ws->side, cudaStreamNonBlocking));
+        ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_scan, cudaEventDisableTiming));
+        ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_huf, cudaEventDisableTiming));
+    }
+    ZK_CUDA_OK(cudaEventRecord(ws->ev_scan, stream));
+    ZK_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_scan, 0));
+    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem, ws->side, a);
+    ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, ws->side));
     ZK_LAUNCH(zk_seq_kernel, gs, 32, seq_smem, stream, a);
-    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem, stream, a);
+    ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_huf, 0));
     // exec stage: ring size / warps per entry chosen from how many entries share the machine
+    // Each entry is one serial dependency chain, so throughput comes from entries in flight: pick warps per
+    // CTA and ring size such that (if possible) every entry of the batch is resident at once.
+    int per_sm = (int)((n + (uint32_t)sms - 1) / (uint32_t)sms);
     int W = exec_warps;
-    uint32_t ring = 32 * 1024;
-    if (W <= 0) { long per = ((long)sms * 32) / (long)n; W = per < 4 ? 4 : (per > 16 ? 16 : (int)per); }
+    if (W <= 0) { W = 16 / per_sm; if (W < 1) W = 1; }
     if (W > 16) W = 16;
-    if ((long)n * 2 <= sms) ring = 128 * 1024; else if ((long)n * 3 <= (long)sms * 2) ring = 64 * 1024;
+    uint32_t ring = 128 * 1024;
+    while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;
     if (ws->ring_override) ring = ws->ring_override;
     ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
     if (verify_checksum) ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a);
