@@ -209,3 +209,115 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
     }
     return worst;
 }
+
+// ---------------------------------------------------------------------------------------------
+// compress
+// ---------------------------------------------------------------------------------------------
+static uint32_t zk_frames_of(size_t n, uint32_t frame_size) {
+    if (n == 0) return 1;                                   // Encoder::finish() always closes one frame (encode.rs:755-756)
+    return (uint32_t)((n + frame_size - 1) / frame_size);
+}
+
+extern "C" int32_t zk_compress_frames_dev(zk_ctx* c, const void* d_src, size_t n, uint32_t frame_size, int32_t level, int32_t checksum,
+                                          void* d_dst, size_t dst_cap, uint32_t* c_sizes, uint32_t* d_sizes, uint32_t frames_cap,
+                                          uint32_t* n_frames, size_t* dst_len, void* cuda_stream) {
+    if (!c || !d_dst || (n && !d_src) || frame_size == 0) return ZK_ERR_INVALID_ARG;
+    if (frame_size > ZK_SEEKABLE_MAX_FRAME_SIZE) frame_size = ZK_SEEKABLE_MAX_FRAME_SIZE;       // encode.rs:531-534
+    if ((n + frame_size - 1) / frame_size > ZK_SEEKABLE_MAX_FRAMES) return ZK_ERR_FRAME_INDEX_TOO_LARGE;
+    const uint32_t nf = zk_frames_of(n, frame_size);
+    if (nf > frames_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
+    ZK_RT_OK(cudaSetDevice(c->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->slot[0].stream;
+    // sub-batches bound the scratch (about 4x the sub-batch input)
+    const size_t sub_bytes = zk_env_size("ZK_DEV_SUB_BYTES", (size_t)1 << 30);
+    uint32_t per = (uint32_t)(sub_bytes / frame_size); if (per == 0) per = 1;
+    cudaEventRecord(c->ev0, st);
+    size_t out_pos = 0;
+    for (uint32_t f0 = 0; f0 < nf; f0 += per) {
+        const uint32_t cnt = nf - f0 < per ? nf - f0 : per;
+        const size_t in_off = (size_t)f0 * frame_size;
+        const size_t in_len = n - in_off < (size_t)cnt * frame_size ? n - in_off : (size_t)cnt * frame_size;
+        size_t produced = 0;
+        int rc = zk_encode_batch(&c->slot[0].ews, st, (const uint8_t*)d_src + in_off, in_len, frame_size, level, checksum,
+                                 (uint8_t*)d_dst + out_pos, dst_cap - out_pos, c_sizes ? c_sizes + f0 : nullptr, cnt, &produced);
+        if (rc) return rc;
+        out_pos += produced;
+    }
+    cudaEventRecord(c->ev1, st);
+    cudaEventSynchronize(c->ev1);
+    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    if (d_sizes) for (uint32_t f = 0; f < nf; f++) {
+        size_t lo = (size_t)f * frame_size; d_sizes[f] = (uint32_t)(n - lo < frame_size ? n - lo : frame_size);
+    }
+    if (n_frames) *n_frames = nf;
+    if (dst_len) *dst_len = out_pos;
+    return 0;
+}
+
+struct ZkSubEnc { uint32_t f0 = 0, cnt = 0; size_t in_off = 0, in_len = 0, out_pos = 0; bool busy = false; };
+
+extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, uint32_t frame_size, int32_t level, int32_t checksum,
+                                      uint8_t* dst, size_t dst_cap, uint32_t* c_sizes, uint32_t* d_sizes, uint32_t frames_cap,
+                                      uint32_t* n_frames, size_t* dst_len) {
+    if (!c || !dst || (n && !src) || frame_size == 0) return ZK_ERR_INVALID_ARG;
+    if (frame_size > ZK_SEEKABLE_MAX_FRAME_SIZE) frame_size = ZK_SEEKABLE_MAX_FRAME_SIZE;
+    if ((n + frame_size - 1) / frame_size > ZK_SEEKABLE_MAX_FRAMES) return ZK_ERR_FRAME_INDEX_TOO_LARGE;
+    const uint32_t nf = zk_frames_of(n, frame_size);
+    if (nf > frames_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
+    ZK_RT_OK(cudaSetDevice(c->device));
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);
+    uint32_t per = (uint32_t)(sub_bytes / frame_size); if (per == 0) per = 1;
+    // The compressed size of a sub-batch is only known when it completes, so output positions are assigned in
+    // order at completion time: H2D and kernels of later sub-batches overlap the D2H of earlier ones.
+    ZkSubEnc sub[ZK_SLOTS];
+    size_t out_pos = 0; int32_t err = 0;
+    std::vector<uint32_t> tmp_sizes(per);
+    auto finish = [&](int si) -> int {
+        ZkSubEnc& sb = sub[si]; ZkSlot& s = c->slot[si];
+        if (!sb.busy) return 0;
+        sb.busy = false;
+        size_t produced = 0;
+        int rc = zk_encode_collect(&s.ews, s.stream, c_sizes ? c_sizes + sb.f0 : tmp_sizes.data(), &produced);
+        if (rc) return rc;
+        if (out_pos + produced > dst_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
+        if (cudaMemcpyAsync(dst + out_pos, s.d_out, produced, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) return ZK_ERR_NO_DEVICE;
+        out_pos += produced;
+        return 0;
+    };
+    uint32_t k = 0;
+    int order[ZK_SLOTS]; int n_inflight = 0;              // completion must follow submission order
+    for (uint32_t f0 = 0; f0 < nf && !err; f0 += per, k++) {
+        const int si = (int)(k % ZK_SLOTS);
+        if (n_inflight == ZK_SLOTS) {                       // oldest in flight is exactly slot si
+            err = finish(si); n_inflight--;
+            if (err) break;
+        }
+        ZkSlot& s = c->slot[si]; ZkSubEnc& sb = sub[si];
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }   // its previous D2H must be done before d_out is reused
+        sb.f0 = f0; sb.cnt = nf - f0 < per ? nf - f0 : per;
+        sb.in_off = (size_t)f0 * frame_size;
+        sb.in_len = n - sb.in_off < (size_t)sb.cnt * frame_size ? n - sb.in_off : (size_t)sb.cnt * frame_size;
+        const size_t bound = zk_encode_bound(sb.in_len, frame_size);
+        int rc = zk_slot_ensure(&s, sb.in_len + 32, bound + 32);
+        if (rc) { err = rc; break; }
+        if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }
+        rc = zk_encode_enqueue(&s.ews, s.stream, s.d_in, sb.in_len, frame_size, level, checksum, s.d_out, bound, sb.cnt);
+        if (rc) { err = rc; break; }
+        sb.busy = true; order[n_inflight++ % ZK_SLOTS] = si;
+    }
+    // drain in submission order
+    for (uint32_t j = 0; j < ZK_SLOTS && !err; j++) {
+        const int si = (int)((k + j) % ZK_SLOTS);          // oldest first
+        int rc = finish(si);
+        if (rc) err = rc;
+    }
+    for (int si = 0; si < ZK_SLOTS; si++) cudaStreamSynchronize(c->slot[si].stream);
+    (void)order;
+    if (err) return err;
+    if (d_sizes) for (uint32_t f = 0; f < nf; f++) {
+        size_t lo = (size_t)f * frame_size; d_sizes[f] = (uint32_t)(n - lo < frame_size ? n - lo : frame_size);
+    }
+    if (n_frames) *n_frames = nf;
+    if (dst_len) *dst_len = out_pos;
+    return 0;
+}
