@@ -67,6 +67,10 @@ uint64_t zk_ctx_kernel_launches(const zk_ctx* ctx);
 /* kernel-only device time (ms, CUDA events on the context's stream) of the most recent batch call */
 float zk_ctx_last_device_ms(const zk_ctx* ctx);
 const char* zk_version(void);
+/* per-kernel device time (CUDA events on the launching stream), accumulated while enabled.
+ * slots: 0 scan, 1 seq, 2 huf, 3 exec, 4 xxh64, 5 match, 6 entropy-enc, 7 frame assembly; arrays of 8 */
+void zk_ctx_profile(zk_ctx* ctx, int32_t enable);
+void zk_ctx_profile_read(const zk_ctx* ctx, float* ms, uint32_t* launches);
 
 /* ------------------------------------------------------------------ batch codec: the hot path */
 /* Upper bound of the compressed size of n input bytes cut into frames of frame_size (excl. seek table). */

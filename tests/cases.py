@@ -1,0 +1,445 @@
+"""Backend-independent test bodies.  Every function takes a zeekstd_b200.Context bound to the library under test
+(the emulated CPU build for `-m "not gpu"`, the real sm_100a build for `-m gpu`) and checks it against the oracle
+(libzstd through the reference's call sequence / the plain-C restatement).  The API tests are ports of the
+reference's own tests (lib/src/lib.rs:69-357, encode.rs:802-871, decode.rs:581-940, seek_table.rs:1061-1278)."""
+from __future__ import annotations
+
+import io
+
+import numpy as np
+
+import zeekstd_b200 as zk
+from oracle import oracle as O
+from util import decode_frames, golden_bytes, golden_meta, offsets, split_frames
+
+INPUT = golden_bytes("dickens_96k.txt")[:12_345]       # plays the role of lib.rs's INPUT (the reference uses its own source text)
+
+
+# ------------------------------------------------------------------------------------------------ raw codec parity
+def check_decode_matches_libzstd(ctx, data: np.ndarray, frame_size: int, level: int, checksum: bool):
+    """libzstd-compressed frames must decode bit-exactly (== ZSTD_decompressStream output == the input)"""
+    frames, cs, ds = O.ref_compress_frames(data, frame_size, level, checksum)
+    out, st, rc = decode_frames(ctx, frames, ds, verify=True)
+    assert rc == 0 and not st.any(), (rc, st[st != 0][:5])
+    assert out == data.tobytes()
+
+
+def check_compress_roundtrip(ctx, data: np.ndarray, frame_size: int, level: int, checksum: bool):
+    """our compressed frames must be spec-compliant: libzstd AND the restatement restore the input; so do we"""
+    comp, cs, ds = ctx.compress_frames(data, frame_size, level, checksum)
+    n_frames = max(1, -(-data.size // frame_size))
+    assert len(cs) == n_frames and int(cs.sum()) == comp.size and int(ds.sum()) == data.size
+    frames = split_frames(comp.tobytes(), cs)
+    for i, fr in enumerate(frames):
+        want = data[i * frame_size: i * frame_size + int(ds[i])].tobytes()
+        assert O.ref_decompress_any(fr, len(want) + 1) == want            # real libzstd accepts it
+        assert O.oracle_decompress(fr, len(want) + 1) == want
+        assert ((fr[4] >> 2) & 1) == int(checksum)                          # Frame_Header_Descriptor checksum bit (encode.rs:861-869)
+    out, st, rc = decode_frames(ctx, frames, ds, verify=True)
+    assert rc == 0 and out == data.tobytes()
+    return data.size / max(1, comp.size)
+
+
+def check_golden_archives(ctx):
+    meta = golden_meta()
+    src = golden_bytes("dickens_96k.txt")
+    for name, info in meta["archives"].items():
+        a = golden_bytes(name + ".zst")
+        dec = zk.Decoder(zk.BytesWrapper(a) if False else zk.DecodeOptions(a, ctx))
+        assert dec.seek_table().num_frames() == info["num_frames"]
+        assert dec.read_all() == src[: info["src_bytes"]], name
+
+
+def check_corruption_is_detected(ctx, trials: int = 24):
+    """flipping bits must never yield silently wrong data when the frame carries a checksum, and must never crash"""
+    x = np.frombuffer(golden_bytes("dickens_96k.txt")[:40_000], dtype=np.uint8)
+    frames, cs, ds = O.ref_compress_frames(x, 40_000, 3, True)
+    good = frames[0]
+    rng = np.random.default_rng(11)
+    detected = 0
+    for _ in range(trials):
+        bad = bytearray(good)
+        pos = int(rng.integers(0, len(bad)))
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        out, st, rc = decode_frames(ctx, [bytes(bad)], ds, verify=True)
+        if rc != 0:
+            detected += 1
+            assert zk.Error(rc, ctx.lib).is_zstd()
+        else:
+            assert out == x.tobytes()          # only harmless flips (e.g. in unused header bits) may pass
+    assert detected >= trials * 0.8
+    # truncated and garbage inputs
+    for blob in (good[:-7], good[: len(good) // 2], b"\x00" * 64, good[:4]):
+        out, st, rc = decode_frames(ctx, [blob], ds, verify=True)
+        assert rc != 0
+
+
+# ------------------------------------------------------------------------------------------------ API: encode side
+def new_seekable(ctx, policy=None, data: bytes = INPUT, out_buf_len=None) -> bytes:
+    """decode.rs:587-629: RawEncoder driven with a caller buffer, then the seek table appended"""
+    enc = zk.EncodeOptions(ctx).frame_size_policy(policy or zk.FrameSizePolicy.default()).into_raw_encoder()
+    buf = bytearray(out_buf_len or max(len(data), 64))
+    seekable = bytearray()
+    in_progress = out_progress = 0
+    while in_progress < len(data):
+        p = enc.compress(data[in_progress:], buf)
+        seekable += buf[: p.out_progress]
+        in_progress += p.in_progress
+        out_progress += p.out_progress
+    assert in_progress == len(data)
+    while True:
+        p = enc.end_frame(buf)
+        seekable += buf[: p.out_progress]
+        out_progress += p.out_progress
+        if p.data_left == 0:
+            break
+    assert out_progress == len(seekable)
+    ser = enc.into_seek_table().into_serializer()
+    while True:
+        n = ser.write_into(buf)
+        if n == 0:
+            break
+        seekable += buf[:n]
+    assert out_progress + ser.encoded_len() == len(seekable)
+    return bytes(seekable)
+
+
+def check_cycle_tiny_buffers(ctx, policy=None):
+    """lib.rs:82-134 test_cycle: every stage in many small steps (buffer = len/500), then full decompression"""
+    data = INPUT
+    a = new_seekable(ctx, policy, data, out_buf_len=max(1, len(data) // 500))
+    # libzstd decodes the frames of our archive
+    st = O.OracleSeekTable.parse(a, "foot")
+    assert O.ref_decompress_any(a[: st.c[-1]], len(data) + 1) == data
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    out = bytearray()
+    buf = bytearray(max(1, len(data) // 500))
+    while True:
+        n = dec.decompress(buf)
+        if n == 0:
+            break
+        out += buf[:n]
+    assert bytes(out) == data
+
+
+def check_standalone_seek_table(ctx):
+    """lib.rs:136-200: seek table kept apart from the frames, Head and Foot"""
+    for fmt in (zk.Format.Head, zk.Format.Foot):
+        enc = zk.EncodeOptions(ctx).frame_size_policy(zk.FrameSizePolicy.Uncompressed(1000)).into_raw_encoder()
+        frames = bytearray()
+        buf = bytearray(4096)
+        pos = 0
+        while pos < len(INPUT):
+            p = enc.compress(INPUT[pos:], buf)
+            frames += buf[: p.out_progress]; pos += p.in_progress
+        while True:
+            p = enc.end_frame(buf)
+            frames += buf[: p.out_progress]
+            if p.data_left == 0:
+                break
+        table = enc.into_seek_table().into_format_serializer(fmt).to_bytes()
+        st = zk.SeekTable.from_bytes(table, fmt, ctx.lib)
+        assert st.size_comp() == len(frames) and st.size_decomp() == len(INPUT)
+        dec = zk.DecodeOptions(bytes(frames), ctx).seek_table(st).into_decoder()
+        assert dec.read_all() == INPUT
+
+
+def check_encoder_decoder_io(ctx, policy=None, chunk: int = 1000):
+    """lib.rs:266-287: std Encoder / Decoder through io copy; finish() returns the bytes written"""
+    sink = io.BytesIO()
+    opts = zk.EncodeOptions(ctx)
+    if policy:
+        opts.frame_size_policy(policy)
+    enc = opts.into_encoder(sink)
+    for i in range(0, len(INPUT), chunk):
+        assert enc.compress(INPUT[i:i + chunk]) == len(INPUT[i:i + chunk])
+    n = enc.finish()
+    a = sink.getvalue()
+    assert n == len(a)
+    st = O.OracleSeekTable.parse(a, "foot")
+    assert st.d[-1] == len(INPUT) and st.c[-1] + 17 + 8 * st.num_frames() == len(a)
+    assert O.ref_decompress_any(a[: st.c[-1]], len(INPUT) + 1) == INPUT
+    dec = zk.Decoder(zk.DecodeOptions(io.BytesIO(a), ctx))       # generic Read + Seek source
+    out = io.BytesIO()
+    while True:
+        b = bytearray(777)
+        k = dec.readinto(b)
+        if not k:
+            break
+        out.write(b[:k])
+    assert out.getvalue() == INPUT
+    return st.num_frames()
+
+
+def check_frame_counts_match_reference(ctx):
+    """frame boundaries are a host-side contract: same (d_size) sequence as the reference for the same policy"""
+    for fs in (1000, len(INPUT), len(INPUT) // 3, 4096):
+        sink = io.BytesIO()
+        enc = zk.EncodeOptions(ctx).frame_size_policy(zk.FrameSizePolicy.Uncompressed(fs)).into_encoder(sink)
+        enc.write(INPUT)
+        enc.finish()
+        ours = O.OracleSeekTable.parse(sink.getvalue(), "foot")
+        _, ref = O.ref_seekable_archive(np.frombuffer(INPUT, dtype=np.uint8), fs, 1, False)
+        assert ours.d == ref.d, fs
+    # empty stream: one empty frame, like Encoder::finish() on no input
+    sink = io.BytesIO()
+    enc = zk.Encoder(sink, zk.EncodeOptions(ctx))
+    enc.finish()
+    ours = O.OracleSeekTable.parse(sink.getvalue(), "foot")
+    _, ref = O.ref_seekable_archive(np.zeros(0, dtype=np.uint8), 0x200000, 1, False)
+    assert ours.d == ref.d == [0, 0] and ours.num_frames() == 1
+    assert O.ref_decompress_any(sink.getvalue()[: ours.c[-1]], 1) == b""
+
+
+def check_raw_encoder_reset(ctx):
+    """encode.rs:810-846: reset_frame + reset_seek_table reproduce an identical seek table"""
+    enc = zk.EncodeOptions(ctx).frame_size_policy(zk.FrameSizePolicy.Uncompressed(2000)).into_raw_encoder()
+    buf = bytearray(len(INPUT) + 1024)
+
+    def run():
+        pos = 0
+        while pos < len(INPUT):
+            p = enc.compress(INPUT[pos:], buf); pos += p.in_progress
+        while enc.end_frame(buf).data_left:
+            pass
+        return enc.seek_table().clone()
+
+    enc.compress(INPUT[:500], buf)
+    enc.reset_frame()
+    a = run()
+    enc.reset_seek_table()
+    assert enc.seek_table().num_frames() == 0
+    b = run()
+    assert a == b and a.num_frames() == -(-len(INPUT) // 2000)
+
+
+def check_checksum_flag(ctx):
+    """encode.rs:848-870: with checksum_flag(true) every frame's descriptor has bit 2 set"""
+    for flag in (True, False):
+        sink = io.BytesIO()
+        enc = zk.EncodeOptions(ctx).checksum_flag(flag).frame_size_policy(zk.FrameSizePolicy.Uncompressed(3000)).into_encoder(sink)
+        enc.write(INPUT); enc.finish()
+        a = sink.getvalue()
+        st = zk.SeekTable.from_bytes(a, zk.Format.Foot, ctx.lib)
+        for i in range(st.num_frames()):
+            assert ((a[st.frame_start_comp(i) + 4] >> 2) & 1) == int(flag)
+
+
+# ------------------------------------------------------------------------------------------------ API: decode side
+def check_decoder_options(ctx):
+    """decode.rs:631-661"""
+    a = new_seekable(ctx)
+    st = zk.SeekTable.from_bytes(a, zk.Format.Foot, ctx.lib)
+    oks = [zk.DecodeOptions(a, ctx), zk.DecodeOptions(a, ctx).lower_frame(st.num_frames() - 1), zk.DecodeOptions(a, ctx).upper_frame(st.num_frames() - 1),
+           zk.DecodeOptions(a, ctx).offset(st.size_decomp()), zk.DecodeOptions(a, ctx).offset_limit(st.size_decomp()),
+           zk.DecodeOptions(bytes([0, 128]), ctx).seek_table(st.clone())]
+    errs = [zk.DecodeOptions(bytes([0, 128]), ctx), zk.DecodeOptions(a, ctx).lower_frame(st.num_frames()), zk.DecodeOptions(a, ctx).upper_frame(st.num_frames()),
+            zk.DecodeOptions(a, ctx).offset(st.size_decomp() + 1), zk.DecodeOptions(a, ctx).offset_limit(st.size_decomp() + 1)]
+    for o in oks:
+        o.into_decoder()
+    for o in errs:
+        try:
+            o.into_decoder()
+            raise AssertionError("expected an error")
+        except zk.Error:
+            pass
+
+
+def check_decoder_state_machine(ctx):
+    """decode.rs:663-939, one body per reference test"""
+    n_in = len(INPUT)
+    out = bytearray(n_in)
+    # decompress_and_reset (:663-682)
+    a = new_seekable(ctx)
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    assert dec.decompress(out) == n_in and bytes(out) == INPUT
+    assert dec.decompress(out) == 0
+    dec.reset()
+    assert dec.decompress(out) == n_in and bytes(out) == INPUT
+    # decompress_until_upper_frame (:684-699)
+    fs = n_in // 7
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(fs)), ctx))
+    dec.set_lower_frame(0); dec.set_upper_frame(5)
+    buf = bytearray(fs * 6)
+    assert dec.decompress(buf) == fs * 6 and bytes(buf) == INPUT[: fs * 6]
+    # decompress_last_frames (:701-716)
+    fs = n_in // 9
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(fs)), ctx))
+    dec.set_lower_frame(5); dec.set_upper_frame(9)
+    ln = n_in - fs * 5
+    buf = bytearray(ln)
+    assert dec.decompress(buf) == ln and bytes(buf) == INPUT[n_in - ln:]
+    # upper_frame_greater_than_lower_frame (:718-730)
+    fs = n_in // 13
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(fs)), ctx))
+    dec.set_lower_frame(9); dec.set_upper_frame(8)
+    assert dec.decompress(out) == 0
+    # reset_decompression (:732-745)
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    dec.decompress(bytearray(128)); dec.reset()
+    assert dec.decompress(out) == n_in and bytes(out) == INPUT
+    # decompress_everything_after_partly_decompression (:747-771)
+    fs = n_in // 32
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(fs)), ctx))
+    dec.set_lower_frame(23); dec.set_upper_frame(29)
+    n = dec.decompress(out)
+    assert n == fs * 30 - fs * 23 and bytes(out[:n]) == INPUT[fs * 23: fs * 30]
+    dec.set_lower_frame(0); dec.set_upper_frame(dec.seek_table().num_frames() - 1)
+    assert dec.decompress(out) == n_in and bytes(out) == INPUT
+    # set_frame_boundaries (:773-795)
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    nf = dec.seek_table().num_frames()
+    dec.set_lower_frame(nf - 1); dec.set_upper_frame(nf - 1)
+    for fn in (dec.set_lower_frame, dec.set_upper_frame):
+        try:
+            fn(nf); raise AssertionError
+        except zk.Error as e:
+            assert e.is_frame_index_too_large()
+    # set_offset_boundaries (:797-819)
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    size = dec.seek_table().size_decomp()
+    dec.set_offset(size); dec.set_offset_limit(size)
+    for fn in (dec.set_offset, dec.set_offset_limit):
+        try:
+            fn(size + 1); raise AssertionError
+        except zk.Error as e:
+            assert e.is_offset_out_of_range()
+    # decompress_within_offset_boundaries (:821-851)
+    fs = n_in // 34
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(fs)), ctx))
+    off = n_in // 3; lim = 2 * off
+    dec.set_offset(off); dec.set_offset_limit(lim)
+    n = dec.decompress(out)
+    assert n == lim - off and bytes(out[:n]) == INPUT[off:lim]
+    assert dec.offset() == lim
+    dec.set_offset(off)                                   # limit persists across set_offset
+    assert dec.decompress(out) == lim - off
+    dec.reset()
+    assert dec.offset() == 0 and dec.offset_limit() == size and dec.read_compressed() == 0
+    assert dec.decompress(out) == n_in and bytes(out) == INPUT
+    # seek (:853-908)
+    fs = n_in // 19
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(fs)), ctx))
+    seek_pos = n_in // 4; end = n_in
+    assert dec.seek(seek_pos, 0) == seek_pos and dec.offset() == seek_pos
+    n = dec.decompress(out)
+    assert dec.read_compressed() != 0 and n == end - seek_pos and bytes(out[:n]) == INPUT[seek_pos:end]
+    assert dec.offset() == end
+    back = -(2 * fs)
+    start = n_in + back
+    assert dec.read_compressed() != 0
+    dec.seek(back, 2)
+    assert dec.offset() == start and dec.read_compressed() == 0
+    n = dec.decompress(out)
+    assert n == end - start and bytes(out[:n]) == INPUT[start:end]
+    dec.seek(-(n_in // 2), 1)                               # SeekFrom::Current
+    assert dec.offset() == n_in - n_in // 2
+    try:
+        dec.seek(1, 2); raise AssertionError                # positive SeekFrom::End is an error (:561-563)
+    except zk.Error as e:
+        assert e.is_offset_out_of_range()
+    # reset_dctx_on_frame_change (:910-939)
+    dec = zk.Decoder(zk.DecodeOptions(new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(100)), ctx))
+    assert dec.read_compressed() == 0
+    dec.set_offset(10)
+    assert dec.readinto(bytearray(10)) == 10
+    assert dec.read_compressed() != 0
+    dec.set_offset(30)                                      # same frame, forward: no reset
+    assert dec.offset() == 30 and dec.read_compressed() != 0
+    n = dec.decompress(out)
+    assert n == n_in - 30 and bytes(out[:n]) == INPUT[30:]
+    dec.set_offset(101)                                     # other frame: reset
+    assert dec.offset() == 101 and dec.read_compressed() == 0
+    n = dec.decompress(out)
+    assert n == n_in - 101 and bytes(out[:n]) == INPUT[101:]
+
+
+def check_libzstd_archive_through_decoder(ctx):
+    """cross-implementation parity the reference lacks: archives written by the reference path
+    (libzstd) are read back bit-exactly through our Decoder, whole and ranged"""
+    data = np.frombuffer(golden_bytes("dickens_96k.txt"), dtype=np.uint8)
+    a, st = O.ref_seekable_archive(data, 10_000, 3, True)
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    assert dec.read_all() == data.tobytes()
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        lo = int(rng.integers(0, data.size)); hi = int(rng.integers(lo, min(data.size, lo + 30_000) + 1))
+        dec.set_offset(lo); dec.set_offset_limit(hi)
+        assert dec.read_all() == data[lo:hi].tobytes()
+        dec.set_offset_limit(data.size)
+
+
+# ------------------------------------------------------------------------------------------------ seek table (host only)
+def check_seek_table(lib):
+    """seek_table.rs:1084-1277 + the known-answer vectors of SURVEY.md 8c, cross-checked against the oracle restatement"""
+    from zeekstd_b200 import _native
+    _native.set_default_lib(lib)
+    st = zk.SeekTable(lib=lib)
+    assert st.into_serializer().to_bytes().hex() == "5e2a4d1809000000" + "00000000" + "00" + "b1ea928f"
+    st.log_frame(123, 456)
+    assert st.into_format_serializer(zk.Format.Foot).to_bytes().hex() == "5e2a4d18110000007b000000c80100000100000000b1ea928f"
+    assert st.into_format_serializer(zk.Format.Head).to_bytes().hex() == "5e2a4d18110000000100000000b1ea928f7b000000c8010000"
+    st.log_frame(333, 444)
+    assert st.into_serializer().to_bytes().hex() == "5e2a4d18190000007b000000c80100004d010000bc0100000200000000b1ea928f"
+    # accessor arithmetic over 1234 frames (:1085-1115)
+    NUM, CS, DS = 1234, 123, 456
+    st = zk.SeekTable(lib=lib); orc = O.OracleSeekTable()
+    for _ in range(NUM):
+        st.log_frame(CS, DS); orc.log_frame(CS, DS)
+    assert st.num_frames() == NUM and st.size_comp() == NUM * CS and st.size_decomp() == NUM * DS
+    assert st.max_frame_size_comp() == CS and st.max_frame_size_decomp() == DS
+    for i in (0, 1, 617, NUM - 1):
+        assert st.frame_start_comp(i) == i * CS and st.frame_end_comp(i) == (i + 1) * CS and st.frame_size_comp(i) == CS
+        assert st.frame_start_decomp(i) == i * DS and st.frame_end_decomp(i) == (i + 1) * DS and st.frame_size_decomp(i) == DS
+        for probe in (i * DS, i * DS + 1, (i + 1) * DS - 1):
+            assert st.frame_index_decomp(probe) == i == orc.frame_index_decomp(probe)
+        assert st.frame_index_comp(i * CS + CS // 2) == i == orc.frame_index_comp(i * CS + CS // 2)
+    assert st.frame_index_decomp(NUM * DS) == NUM - 1 and st.frame_index_decomp(NUM * DS + 99) == NUM - 1
+    for fn in (st.frame_start_comp, st.frame_end_decomp, st.frame_size_comp):
+        try:
+            fn(NUM); raise AssertionError
+        except zk.Error as e:
+            assert e.is_frame_index_too_large()
+    # resumable serialization with tiny buffers (:1117-1141, 1257-1260), both formats, vs the oracle bytes
+    for fmt, name in ((zk.Format.Foot, "foot"), (zk.Format.Head, "head")):
+        want = orc.serialize(name)
+        for blen in (1, 2, 3, 7, 8, 9, 13, 63):
+            ser = st.into_format_serializer(fmt)
+            got = bytearray()
+            while True:
+                b = bytearray(blen)
+                n = ser.write_into(b)
+                if n == 0:
+                    break
+                got += b[:n]
+            assert bytes(got) == want and ser.encoded_len() == len(want)
+            ser.reset()
+            assert ser.to_bytes() == want
+        # serde cycle (:1143-1154)
+        back = zk.SeekTable.from_bytes(want, fmt, lib)
+        assert back == st
+    for nframes in (0, 1, 2, 1023, 1024, 1025, 4095):
+        t = zk.SeekTable(lib=lib)
+        for i in range(nframes):
+            t.log_frame(i * 7 + 1, i * 13 + 5)
+        for fmt in (zk.Format.Head, zk.Format.Foot):
+            assert zk.SeekTable.from_bytes(t.into_format_serializer(fmt).to_bytes(), fmt, lib) == t
+    # entries with per-frame checksums (12 bytes, descriptor bit 7), as zstd's own C seekable code writes (:1187-1212)
+    import struct
+    body = b"".join(struct.pack("<III", 100 + i, 1000 + i, 0xDEADBEEF) for i in range(5))
+    tbl = struct.pack("<II", 0x184D2A5E, len(body) + 9) + body + struct.pack("<IBI", 5, 0x80, 0x8F92EAB1)
+    t = zk.SeekTable.from_bytes(b"x" * 33 + tbl, zk.Format.Foot, lib)
+    assert t.num_frames() == 5 and t.frame_size_comp(4) == 104 and t.frame_size_decomp(4) == 1004
+    # malformed tables
+    good = st.into_serializer().to_bytes()
+    for mutate, pred in ((lambda b: b[:-1] + b"\x00", "zstd10"), (lambda b: b[:-5] + b"\x04" + b[-4:], "zstd20"),
+                         (lambda b: b"\x00" + b[1:], "zstd10"), (lambda b: b[:4] + b"\x01\x00\x00\x00" + b[8:], "zstd20"),
+                         (lambda b: b[-8:], "range")):
+        try:
+            zk.SeekTable.from_bytes(mutate(good), zk.Format.Foot, lib)
+            raise AssertionError("malformed table accepted")
+        except zk.Error as e:
+            if pred == "range":
+                assert e.is_offset_out_of_range()
+            else:
+                assert e.is_zstd() and e.zstd_code() == int(pred[4:])

@@ -277,6 +277,11 @@ template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int x, in
     if ((s & ~(width - 1)) != (lane & ~(width - 1))) s = lane;
     return emu_unpack<T>(o[s]);
 }
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+    const uint64_t* o = emu::warp_exchange(mask, v); unsigned r = 0;
+    for (int l = 0; l < 32; l++) if (((mask >> l) & 1) && (unsigned)o[l] == v) r |= 1u << l;
+    return r;
+}
 static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     const uint64_t* o = emu::warp_exchange(mask, v); unsigned r = 0;
     for (int l = 0; l < 32; l++) if ((mask >> l) & 1) r += (unsigned)o[l];

@@ -1,0 +1,61 @@
+"""The C-ABI library loads and exports every symbol include/zeekstd_b200.h declares (no compute calls: no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    h = open(os.path.join(ROOT, "include", "zeekstd_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    names = set(re.findall(r"\b(zk_[a-z0-9_]+)\s*\(", h))
+    names -= {"zk_write_fn", "zk_flush_fn"}
+    return sorted(names)
+
+
+def test_header_and_binding_agree():
+    from zeekstd_b200 import _native
+    assert declared_symbols() == _native.EXPORTED_SYMBOLS
+
+
+def test_product_library_exports_every_symbol():
+    from zeekstd_b200 import _native
+    from zeekstd_b200.build import build_product
+    so = build_product()                      # nvcc cross-compiles for sm_100a without a GPU
+    lib = _native.load(so)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.zk_version()
+
+
+def test_product_library_contains_sm100a_sass():
+    import subprocess
+    from zeekstd_b200 import _native
+    out = subprocess.run(["cuobjdump", "-lelf", _native.PRODUCT_SO], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    import ctypes
+    import torch
+    from zeekstd_b200 import _native
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _native.load(_native.PRODUCT_SO)
+    h = ctypes.c_void_p()
+    rc = lib.zk_ctx_create(0, 0, ctypes.byref(h))
+    assert rc == -1005 and not h.value        # ZK_ERR_NO_DEVICE
+
+
+def test_product_never_links_the_oracle():
+    import subprocess
+    from zeekstd_b200 import _native
+    out = subprocess.run(["nm", "-D", _native.PRODUCT_SO], capture_output=True, text=True).stdout
+    assert "zko_" not in out and "zkr_" not in out and "ZSTD_" not in out
+    for d, _, files in os.walk(os.path.join(ROOT, "zeekstd_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                txt = open(os.path.join(d, f)).read()
+                assert "zko_" not in txt and "zkr_" not in txt and "dlopen" not in txt and "libzstd.so" not in txt, f

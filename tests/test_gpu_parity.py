@@ -1,0 +1,160 @@
+"""`-m gpu`: the parity tests proper, through the C ABI of the real sm_100a library on a B200.
+Same bodies as the emulated suite (tests/cases.py) at realistic sizes, the committed golden fixtures, and -- at
+BASELINE.json's full sizes -- size-independent properties (round trips, libzstd cross-decoding)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import zeekstd_b200 as zk
+from oracle import oracle as O
+from util import decode_frames, make_ctx, offsets, split_frames
+from zeekstd_b200 import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(gpu_lib):
+    c = make_ctx(gpu_lib)
+    yield c
+    c.close()
+
+
+def test_native_library_is_the_one_running(ctx, gpu_lib):
+    assert b"sm_100a" in gpu_lib.zk_version()
+    before = ctx.kernel_launches
+    cases.check_compress_roundtrip(ctx, corpus.make_class("text", 100_000, 1).numpy(), 50_000, 3, True)
+    assert ctx.kernel_launches > before
+
+
+@pytest.mark.parametrize("kind", ["text", "structured", "lowent", "random", "runs"])
+@pytest.mark.parametrize("level,fs,ck", [(1, 2 << 20, False), (3, 512 << 10, True), (7, 1 << 20, True), (19, 300_000, False)])
+def test_decode_matches_libzstd(ctx, kind, level, fs, ck):
+    n = (6 << 20) if level < 19 else (1 << 20)
+    cases.check_decode_matches_libzstd(ctx, corpus.make_class(kind, n, seed=level).numpy(), fs, level, ck)
+
+
+def test_decode_frame_size_sweep(ctx):
+    x = corpus.make_mix(1 << 20, seed=5, segment=32 << 10).numpy()
+    for fs in (1, 10, 123, 3_000, 100_000, 1 << 20):              # cli/tests/integration/main.rs:10,146-179 frame sizes
+        n = min(x.size, fs * 300)
+        cases.check_decode_matches_libzstd(ctx, x[:n], fs, 3, fs % 2 == 0)
+
+
+@pytest.mark.parametrize("kind", ["text", "structured", "lowent", "random", "runs"])
+@pytest.mark.parametrize("level,fs,ck", [(1, 2 << 20, False), (3, 512 << 10, True)])
+def test_compress_roundtrip(ctx, kind, level, fs, ck):
+    r = cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 6 << 20, seed=7).numpy(), fs, level, ck)
+    assert r >= 0.99
+
+
+def test_compress_edge_sizes(ctx):
+    x = corpus.make_class("text", 300_000, 9).numpy()
+    for n, fs in ((0, 100), (1, 100), (15, 100), (16, 16), (31, 100), (100, 100), (101, 100), (32_767, 1 << 20), (32_768, 32_768), (32_769, 65_536),
+                  (65_537, 1 << 20), (300_000, 1), (300_000, 7), (300_000, 99_999)):
+        if fs < 8:
+            n = min(n, 3_000)
+        cases.check_compress_roundtrip(ctx, x[:n], fs, 3, n % 2 == 0)
+
+
+def test_compress_is_deterministic(ctx):
+    x = corpus.make_mix(8 << 20, seed=3).numpy()
+    a = ctx.compress_frames(x, 1 << 20, 1, True)[0].tobytes()
+    b = ctx.compress_frames(x, 1 << 20, 1, True)[0].tobytes()
+    assert hashlib.sha256(a).digest() == hashlib.sha256(b).digest()
+
+
+def test_golden_archives(ctx):
+    cases.check_golden_archives(ctx)
+
+
+def test_corruption_detected(ctx):
+    cases.check_corruption_is_detected(ctx, trials=60)
+
+
+def test_api_encode_side(ctx):
+    cases.check_cycle_tiny_buffers(ctx)
+    cases.check_cycle_tiny_buffers(ctx, zk.FrameSizePolicy.Uncompressed(777))
+    cases.check_standalone_seek_table(ctx)
+    assert cases.check_encoder_decoder_io(ctx) == 1
+    assert cases.check_encoder_decoder_io(ctx, zk.FrameSizePolicy.Uncompressed(1000), chunk=333) == 13
+    cases.check_frame_counts_match_reference(ctx)
+    cases.check_raw_encoder_reset(ctx)
+    cases.check_checksum_flag(ctx)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 100, 511, 1023])
+def test_frame_size_policies_property(ctx, n):
+    cases.check_encoder_decoder_io(ctx, zk.FrameSizePolicy.Uncompressed(n), chunk=997)
+    cases.check_encoder_decoder_io(ctx, zk.FrameSizePolicy.Compressed(n), chunk=4096)
+
+
+def test_api_decode_side(ctx):
+    cases.check_decoder_options(ctx)
+    cases.check_decoder_state_machine(ctx)
+    cases.check_libzstd_archive_through_decoder(ctx)
+
+
+def test_seek_table(gpu_lib):
+    cases.check_seek_table(gpu_lib)
+
+
+def test_encoder_batches_many_frames(ctx):
+    """Encoder<W> hands whole batches of frames to the GPU; archive must equal frame-by-frame semantics"""
+    import io
+    x = corpus.make_mix(40 << 20, seed=2).numpy()
+    sink = io.BytesIO()
+    enc = zk.EncodeOptions(ctx).frame_size_policy(zk.FrameSizePolicy.Uncompressed(256 << 10)).checksum_flag(True).into_encoder(sink)
+    for i in range(0, x.size, 1 << 20):
+        enc.write(x[i:i + (1 << 20)])
+    total = enc.finish()
+    a = sink.getvalue()
+    assert total == len(a)
+    st = O.OracleSeekTable.parse(a, "foot")
+    assert st.num_frames() == 160 and st.d[-1] == x.size
+    out, sizes = O.ref_decompress_frames(np.frombuffer(a, dtype=np.uint8), st.c, st.d, threads=os.cpu_count())
+    assert out.tobytes() == x.tobytes()
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    dec.set_offset(13 << 20); dec.set_offset_limit((13 << 20) + 65536)
+    assert dec.read_all() == x[13 << 20: (13 << 20) + 65536].tobytes()
+
+
+def test_full_size_roundtrip_properties(ctx):
+    """BASELINE configs[1] size: 1 GiB, 2 MiB frames, level 1 -- compress on the GPU, decode with libzstd on all cores AND on
+    the GPU; plus libzstd-compressed frames decoded on the GPU (bit-exact vs the reference decoder's output == the input)"""
+    import torch
+    n = int(os.environ.get("ZK_TEST_FULL_BYTES", str(1 << 30)))
+    x = corpus.make_mix(n, seed=20260924, device="cuda").cpu().numpy()
+    comp, cs, ds = ctx.compress_frames(x, 2 << 20, 1, False)
+    assert len(cs) == n // (2 << 20) and int(ds.sum()) == n
+    out, sizes = O.ref_decompress_frames(comp, offsets(cs), offsets(ds), threads=os.cpu_count())
+    assert sizes == [int(d) for d in ds] and hashlib.sha256(out.tobytes()).digest() == hashlib.sha256(x.tobytes()).digest()
+    back, st, rc = ctx.decompress_frames(comp, offsets(cs), offsets(ds), True)
+    assert rc == 0 and np.array_equal(back, x)
+    frames, rcs, rds = O.ref_compress_frames(x, 2 << 20, 1, False, threads=os.cpu_count())
+    back, st, rc = ctx.decompress_frames(np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8), offsets(rcs), offsets(rds), True)
+    assert rc == 0 and np.array_equal(back, x)
+
+
+def test_many_small_frames(ctx):
+    """config-3-like: high frame count (512 KiB frames of text), libzstd-compressed, GPU decode bit-exact"""
+    x = corpus.make_text(256 << 20, seed=7, device="cuda").cpu().numpy()
+    frames, cs, ds = O.ref_compress_frames(x, 512 << 10, 1, False, threads=os.cpu_count())
+    back, st, rc = ctx.decompress_frames(np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8), offsets(cs), offsets(ds), False)
+    assert rc == 0 and np.array_equal(back, x)
+
+
+def test_random_offset_reads(ctx):
+    """config-5-like: random 64 KiB reads through set_offset / set_offset_limit on a libzstd-written archive"""
+    x = corpus.make_mix(128 << 20, seed=9, device="cuda").cpu().numpy()
+    a, st = O.ref_seekable_archive(x, 2 << 20, 1, False, threads=os.cpu_count())
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        o = int(rng.integers(0, x.size - 65536))
+        dec.set_offset(o); dec.set_offset_limit(o + 65536)
+        assert dec.read_all() == x[o:o + 65536].tobytes()
+        dec.set_offset_limit(x.size)

@@ -1,0 +1,106 @@
+"""`-m "not gpu"` suite: the host layer and the kernel LOGIC, run on the emulated build of the same sources
+(tests/emul: device code interpreted on the CPU).  Inputs are tiny because every CUDA thread is a coroutine here; the
+same bodies (tests/cases.py) run at realistic sizes on the B200 in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import cases
+import zeekstd_b200 as zk
+from util import make_ctx
+from zeekstd_b200 import corpus
+
+
+@pytest.fixture(scope="module")
+def ctx(emul_lib):
+    c = make_ctx(emul_lib)
+    yield c
+    c.close()
+
+
+def test_seek_table(emul_lib):
+    cases.check_seek_table(emul_lib)
+
+
+@pytest.mark.parametrize("kind,level,fs,ck", [("text", 1, 20_000, False), ("text", 3, 9_000, True), ("structured", 3, 30_000, True),
+                                               ("lowent", 5, 30_000, False), ("random", 1, 8_000, True), ("runs", 3, 30_000, True),
+                                               ("text", 19, 30_000, True)])
+def test_decode_matches_libzstd(ctx, kind, level, fs, ck):
+    cases.check_decode_matches_libzstd(ctx, corpus.make_class(kind, 30_000, seed=level).numpy(), fs, level, ck)
+
+
+def test_decode_tiny_frames_and_empty(ctx):
+    x = corpus.make_class("text", 3_000, 1).numpy()
+    cases.check_decode_matches_libzstd(ctx, x, 100, 3, False)     # 1-stream Huffman / raw literals / predefined tables
+    cases.check_decode_matches_libzstd(ctx, x[:1], 100, 1, True)
+
+
+@pytest.mark.parametrize("kind,level,fs,ck", [("text", 3, 40_000, True), ("text", 1, 11_000, False), ("structured", 3, 40_000, False),
+                                               ("lowent", 3, 40_000, True), ("random", 3, 40_000, True), ("runs", 3, 40_000, True)])
+def test_compress_roundtrip(ctx, kind, level, fs, ck):
+    cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 40_000, seed=3).numpy(), fs, level, ck)
+
+
+def test_compress_edge_sizes(ctx):
+    x = corpus.make_class("text", 70_000, 9).numpy()
+    for n, fs in ((0, 100), (1, 100), (31, 100), (100, 100), (101, 100), (32_768, 32_768), (32_769, 65_536), (65_537, 1 << 20)):
+        cases.check_compress_roundtrip(ctx, x[:n], fs, 3, True)
+
+
+def test_golden_archives(ctx):
+    cases.check_golden_archives(ctx)
+
+
+def test_corruption_detected(ctx):
+    cases.check_corruption_is_detected(ctx, trials=12)
+
+
+def test_cycle_tiny_buffers(ctx):
+    cases.check_cycle_tiny_buffers(ctx)
+    cases.check_cycle_tiny_buffers(ctx, zk.FrameSizePolicy.Uncompressed(777))
+
+
+def test_standalone_seek_table(ctx):
+    cases.check_standalone_seek_table(ctx)
+
+
+def test_encoder_decoder_io(ctx):
+    assert cases.check_encoder_decoder_io(ctx) == 1
+    assert cases.check_encoder_decoder_io(ctx, zk.FrameSizePolicy.Uncompressed(1000), chunk=333) == 13
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 100, 1023])
+def test_frame_size_policies_property(ctx, n):
+    """lib.rs:315-357 proptests: frames as small as one byte, both policies"""
+    cases.check_encoder_decoder_io(ctx, zk.FrameSizePolicy.Uncompressed(max(n, 40)), chunk=97)
+    cases.check_encoder_decoder_io(ctx, zk.FrameSizePolicy.Compressed(n * 8), chunk=4096)
+
+
+def test_one_byte_frames(ctx):
+    data = cases.INPUT[:40]
+    a = cases.new_seekable(ctx, zk.FrameSizePolicy.Uncompressed(1), data)
+    dec = zk.Decoder(zk.DecodeOptions(a, ctx))
+    assert dec.seek_table().num_frames() == 40 and dec.read_all() == data
+
+
+def test_frame_counts_match_reference(ctx):
+    cases.check_frame_counts_match_reference(ctx)
+
+
+def test_raw_encoder_reset(ctx):
+    cases.check_raw_encoder_reset(ctx)
+
+
+def test_checksum_flag(ctx):
+    cases.check_checksum_flag(ctx)
+
+
+def test_decoder_options(ctx):
+    cases.check_decoder_options(ctx)
+
+
+def test_decoder_state_machine(ctx):
+    cases.check_decoder_state_machine(ctx)
+
+
+def test_libzstd_archive_through_decoder(ctx):
+    cases.check_libzstd_archive_through_decoder(ctx)

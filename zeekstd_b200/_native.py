@@ -47,6 +47,8 @@ _SIGS = {
     "zk_ctx_kernel_launches": (c_uint64, [c_void_p]),
     "zk_ctx_last_device_ms": (c_float, [c_void_p]),
     "zk_compress_bound": (c_size_t, [c_size_t, c_uint32]),
+    "zk_ctx_profile": (None, [c_void_p, c_int32]),
+    "zk_ctx_profile_read": (None, [c_void_p, POINTER(c_float), u32p]),
     "zk_compress_frames": (c_int32, [c_void_p, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_void_p, c_size_t,
                                      u32p, u32p, c_uint32, u32p, POINTER(c_size_t)]),
     "zk_decompress_frames": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, c_int32, i32p]),
@@ -134,7 +136,7 @@ _default: ctypes.CDLL | None = None
 
 
 def load(path: str | None = None, require_all: bool = True) -> ctypes.CDLL:
-    """dlopen a build of the native library and attach prototypes. Raises if it cannot be loaded."""
+    """load a build of the native library and attach prototypes. Raises if it cannot be loaded."""
     path = os.path.abspath(path or PRODUCT_SO)
     if path in _libs:
         return _libs[path]

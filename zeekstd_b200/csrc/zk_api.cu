@@ -115,6 +115,22 @@ extern "C" uint64_t zk_ctx_kernel_launches(const zk_ctx* c) { return c ? c->laun
 extern "C" float zk_ctx_last_device_ms(const zk_ctx* c) { return c ? c->last_ms : 0.f; }
 extern "C" size_t zk_compress_bound(size_t n, uint32_t frame_size) { return zk_encode_bound(n, frame_size); }
 
+extern "C" void zk_ctx_profile(zk_ctx* c, int32_t enable) {
+    if (!c) return;
+    for (int i = 0; i < ZK_SLOTS; i++) {
+        c->slot[i].dws.prof.enabled = enable != 0; c->slot[i].ews.prof.enabled = enable != 0;
+        for (int k = 0; k < ZK_PROF_SLOTS; k++) { c->slot[i].dws.prof.ms[k] = c->slot[i].ews.prof.ms[k] = 0.f; c->slot[i].dws.prof.count[k] = c->slot[i].ews.prof.count[k] = 0; }
+    }
+}
+extern "C" void zk_ctx_profile_read(const zk_ctx* c, float* ms, uint32_t* launches) {
+    for (int k = 0; k < ZK_PROF_SLOTS; k++) {
+        float t = 0.f; uint32_t n = 0;
+        for (int i = 0; c && i < ZK_SLOTS; i++) { t += c->slot[i].dws.prof.ms[k] + c->slot[i].ews.prof.ms[k]; n += c->slot[i].dws.prof.count[k] + c->slot[i].ews.prof.count[k]; }
+        if (ms) ms[k] = t;
+        if (launches) launches[k] = n;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // decompress
 // ---------------------------------------------------------------------------------------------

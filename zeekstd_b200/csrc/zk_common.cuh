@@ -21,6 +21,31 @@
 #include <stdint.h>
 #include <stddef.h>
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+// slots: 0 scan, 1 seq, 2 huf, 3 exec, 4 xxh64(dec), 5 match, 6 entropy-enc, 7 frame assembly
+#define ZK_PROF_SLOTS 8
+struct ZkProf {
+    bool enabled = false;
+    cudaEvent_t ev[ZK_PROF_SLOTS][2] = {};
+    bool used[ZK_PROF_SLOTS] = {};
+    float ms[ZK_PROF_SLOTS] = {};
+    unsigned count[ZK_PROF_SLOTS] = {};
+    void begin(int slot, cudaStream_t st) {
+        if (!enabled) return;
+        if (!ev[slot][0]) { cudaEventCreate(&ev[slot][0]); cudaEventCreate(&ev[slot][1]); }
+        cudaEventRecord(ev[slot][0], st);
+    }
+    void end(int slot, cudaStream_t st) { if (!enabled) return; cudaEventRecord(ev[slot][1], st); used[slot] = true; }
+    void harvest() {                        // call after the stream(s) were synchronised
+        if (!enabled) return;
+        for (int i = 0; i < ZK_PROF_SLOTS; i++) if (used[i]) {
+            float t = 0.f; cudaEventSynchronize(ev[i][1]); cudaEventElapsedTime(&t, ev[i][0], ev[i][1]);
+            ms[i] += t; count[i]++; used[i] = false;
+        }
+    }
+    void destroy() { for (int i = 0; i < ZK_PROF_SLOTS; i++) for (int j = 0; j < 2; j++) if (ev[i][j]) { cudaEventDestroy(ev[i][j]); ev[i][j] = nullptr; } }
+};
+
 // libzstd's numeric error codes (ZSTD_ErrorCode); the C ABI reports -(code) so that the
 // reference's Error::is_zstd()/get_error_name() semantics carry over (error.rs:40-45, 101-113).
 enum ZkZstdCode : int {

@@ -1051,6 +1051,7 @@ void zk_decode_ws_free(ZkDecodeWs* ws) {
     if (ws->side) cudaStreamDestroy(ws->side);
     if (ws->ev_scan) cudaEventDestroy(ws->ev_scan);
     if (ws->ev_huf) cudaEventDestroy(ws->ev_huf);
+    ws->prof.destroy();
     *ws = ZkDecodeWs();
 }
 
@@ -1121,7 +1122,9 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     a.lit = ws->lit; a.seq_lit_end = ws->seq_lit_end; a.seq_out_end = ws->seq_out_end; a.seq_off = ws->seq_off;
     a.huf_list = ws->huf_list; a.seq_list = ws->seq_list;
     a.cap_blocks = ws->cap_blocks; a.cap_lit = ws->cap_lit - 64; a.cap_seq = ws->cap_seq;
+    ws->prof.begin(0, stream);
     ZK_LAUNCH(zk_scan_kernel, (n + 127) / 128, 128, 0, stream, a);
+    ws->prof.end(0, stream);
     // entropy stage: persistent warp-CTAs pulling groups of blocks from a work counter
     size_t est_blocks = (size_t)(total_d / ZK_BLOCK_MAX) + n;
     const size_t seq_smem = sizeof(ZkSeqSlot) * ZK_SEQ_LANES, huf_smem = sizeof(ZkHufSlot) * ZK_HUF_SLOTS;
@@ -1143,9 +1146,13 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     }
     ZK_CUDA_OK(cudaEventRecord(ws->ev_scan, stream));
     ZK_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_scan, 0));
+    ws->prof.begin(2, ws->side);
     ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem, ws->side, a);
+    ws->prof.end(2, ws->side);
     ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, ws->side));
+    ws->prof.begin(1, stream);
     ZK_LAUNCH(zk_seq_kernel, gs, 32, seq_smem, stream, a);
+    ws->prof.end(1, stream);
     ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_huf, 0));
     // exec stage: ring size / warps per entry chosen from how many entries share the machine
     // Each entry is one serial dependency chain, so throughput comes from entries in flight: pick warps per
@@ -1157,8 +1164,10 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     uint32_t ring = 128 * 1024;
     while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;
     if (ws->ring_override) ring = ws->ring_override;
+    ws->prof.begin(3, stream);
     ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
-    if (verify_checksum) ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a);
+    ws->prof.end(3, stream);
+    if (verify_checksum) { ws->prof.begin(4, stream); ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a); ws->prof.end(4, stream); }
     ZK_CUDA_OK(cudaMemcpyAsync(ws->h_entries, ws->entries, (size_t)n * sizeof(ZkEntry), cudaMemcpyDeviceToHost, stream));
     ZK_CUDA_OK(cudaMemcpyAsync(ws->h_counters, ws->counters, sizeof(ZkCounters), cudaMemcpyDeviceToHost, stream));
     ws->launches += 4 + (verify_checksum ? 1 : 0);
@@ -1176,6 +1185,7 @@ int zk_decode_collect(ZkDecodeWs* ws, cudaStream_t stream, int32_t* status_out) 
     if (cudaGetLastError() != cudaSuccess) return -(int)ZKZ_GENERIC;
 #endif
     ws->pending_n = 0;
+    ws->prof.harvest();
     if (ws->h_counters->overflow) {
         ws->want_blocks = (size_t)ws->h_counters->n_blocks; ws->want_lit = (size_t)ws->h_counters->n_lit; ws->want_seq = (size_t)ws->h_counters->n_seq;
         return ZK_ST_RETRY;

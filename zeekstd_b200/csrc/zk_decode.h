@@ -30,6 +30,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint32_t pending_n = 0;
     int sm_count = 0;
     unsigned long long launches = 0;  // kernels launched so far (bench.py's gpu_launches)
+    ZkProf prof;
 };
 
 // Decode n seek-table entries.  d_comp / d_dst are device pointers (16-byte aligned, 16 readable bytes of

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         if (a.level >= 2) {
             for (size_t p0 = base; p0 < lo; p0 += 32) {
                 const size_t p = p0 + lane;
-                if (p < lo) table[zkc_hash5(zkc_ld8(src + p))] = (uint16_t)(p - base);
+                const uint32_t hh = p < lo ? zkc_hash5(zkc_ld8(src + p)) : (0xFFFF0000u | (uint32_t)lane);
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, hh);
+                if (p < lo && lane == 31 - __clz((int)same)) table[hh] = (uint16_t)(p - base);
             }
             __syncwarp();
         }
@@ -103,7 +105,10 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
             unsigned long long cur = 0; uint32_t h = 0, cand = 0;
             if (valid) { cur = zkc_ld8(src + p); h = zkc_hash5(cur); cand = table[h]; }
             __syncwarp();
-            if (valid) table[h] = (uint16_t)(p - base);
+            // several lanes may hash to the same slot: the highest position wins, as sequential insertion would leave it
+            // (keeps the compressed bytes deterministic)
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, valid ? h : (0xFFFF0000u | (uint32_t)lane));
+            if (valid && lane == 31 - __clz((int)same)) table[h] = (uint16_t)(p - base);
             // candidate from the hash table, and the repeat-offset candidate
             uint32_t moff = 0, mlen0 = 0;
             if (valid) {
@@ -827,6 +832,7 @@ size_t zk_encode_bound(size_t n, uint32_t frame_size) {
 void zk_encode_ws_free(ZkEncodeWs* ws) {
     if (ws->buf) cudaFree(ws->buf);
     if (ws->h_sizes) cudaFreeHost(ws->h_sizes);
+    ws->prof.destroy();
     *ws = ZkEncodeWs();
 }
 
@@ -877,12 +883,18 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     a.frame_csize = (uint32_t*)(base + o_fcs); a.frame_off = (unsigned long long*)(base + o_foff); a.frame_hash = (uint32_t*)(base + o_fh);
     a.dst = d_dst; a.dst_cap = dst_cap; a.total = (unsigned long long*)(base + o_tot); a.error = (uint32_t*)(base + o_tot + 8);
     ZKC_CUDA_OK(cudaMemsetAsync(base + o_tot, 0, 16, stream));
+    ws->prof.begin(5, stream);
     ZK_LAUNCH(zk_match_kernel, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
+    ws->prof.end(5, stream);
+    ws->prof.begin(6, stream);
     ZK_LAUNCH(zk_entropy_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
+    ws->prof.end(6, stream);
+    ws->prof.begin(7, stream);
     if (checksum) ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, stream, a);
     ZK_LAUNCH(zk_frame_size_kernel, (n_frames + 255) / 256, 256, 0, stream, a);
     ZK_LAUNCH(zk_frame_scan_kernel, 1, 1024, 0, stream, a);
     ZK_LAUNCH(zk_frame_gather_kernel, (uint32_t)((n_blocks + 3) / 4), 128, 0, stream, a);
+    ws->prof.end(7, stream);
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes, a.frame_csize, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, stream));
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes + ws->cap_frames, a.total, 16, cudaMemcpyDeviceToHost, stream));
     ws->launches += 5 + (checksum ? 1 : 0);
@@ -898,6 +910,7 @@ int zk_encode_collect(ZkEncodeWs* ws, cudaStream_t stream, uint32_t* c_sizes, si
     if (cudaGetLastError() != cudaSuccess) return -(int)ZKZ_GENERIC;
 #endif
     ws->pending_frames = 0;
+    ws->prof.harvest();
     unsigned long long total; uint32_t err;
     memcpy(&total, ws->h_sizes + ws->cap_frames, 8);
     memcpy(&err, (uint8_t*)(ws->h_sizes + ws->cap_frames) + 8, 4);

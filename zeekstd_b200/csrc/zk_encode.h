@@ -8,6 +8,7 @@ struct ZkEncodeWs {                    // HBM scratch owned by a zk_ctx slot, gr
     int sm_count = 0;
     unsigned long long launches = 0;
     uint32_t pending_frames = 0;
+    ZkProf prof;
 };
 
 // Compress n bytes at d_src into ceil(n/frame_size) frames written back to back at d_dst.
