@@ -12,11 +12,14 @@
 #define ZK_RT_OK(x) do { (void)(x); } while (0)
 #endif
 
+static int zk_host_slots();
 static size_t zk_env_size(const char* name, size_t dflt) {
     const char* s = getenv(name);
     if (!s || !*s) return dflt;
     return (size_t)strtoull(s, nullptr, 10);
 }
+
+static int zk_host_slots() { size_t v = zk_env_size("ZK_HOST_SLOTS", 4); return (int)(v < 1 ? 1 : (v > ZK_SLOTS ? ZK_SLOTS : v)); }
 
 extern "C" const char* zk_version(void) {
 #ifdef ZK_EMUL
@@ -207,10 +210,11 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
     ZK_RT_OK(cudaSetDevice(c->device));
     const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);
     ZkSubDec sub[ZK_SLOTS];
+    const int NS = zk_host_slots();
     int32_t worst = 0;
     uint32_t k = 0;
     for (uint32_t first = 0; first < n; k++) {
-        int si = (int)(k % ZK_SLOTS);
+        int si = (int)(k % NS);
         int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
         if (rc && !worst) worst = rc;
         uint32_t end = zk_next_sub(d_off, first, n, sub_bytes, 1u << 20);
@@ -301,10 +305,11 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         return 0;
     };
     uint32_t k = 0;
+    const int NS = zk_host_slots();
     int order[ZK_SLOTS]; int n_inflight = 0;              // completion must follow submission order
     for (uint32_t f0 = 0; f0 < nf && !err; f0 += per, k++) {
-        const int si = (int)(k % ZK_SLOTS);
-        if (n_inflight == ZK_SLOTS) {                       // oldest in flight is exactly slot si
+        const int si = (int)(k % NS);
+        if (n_inflight == NS) {                             // oldest in flight is exactly slot si
             err = finish(si); n_inflight--;
             if (err) break;
         }
@@ -322,8 +327,8 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         sb.busy = true; order[n_inflight++ % ZK_SLOTS] = si;
     }
     // drain in submission order
-    for (uint32_t j = 0; j < ZK_SLOTS && !err; j++) {
-        const int si = (int)((k + j) % ZK_SLOTS);          // oldest first
+    for (uint32_t j = 0; j < (uint32_t)NS && !err; j++) {
+        const int si = (int)((k + j) % NS);                // oldest first
         int rc = finish(si);
         if (rc) err = rc;
     }

@@ -327,48 +327,55 @@ struct ZkcC2Smem {
     uint32_t scratch[16];
 };
 
-// Huffman code lengths limited to 11 bits (lane 0).  Returns max code length (0 = not compressible as Huffman).
-__device__ int zkc_huf_build(ZkcC2Smem& sm, uint32_t nlit) {
-    // symbols present, sorted by count ascending (insertion into a small array; <= 256 symbols)
-    uint16_t order[256]; int n = 0;
-    for (int s = 0; s < 256; s++) if (sm.hist[s]) order[n++] = (uint16_t)s;
+// Huffman code lengths limited to 11 bits.  Whole warp: the symbols are ranked by count with an all-pairs comparison
+// in shared memory (each lane ranks 8 symbols), then lane 0 runs the two-queue tree build on shared-memory arrays
+// (aliasing the bit buffer, which is not in use yet).  Returns max code length (0 = fewer than two symbols).
+__device__ int zkc_huf_build(ZkcC2Smem& sm, int lane) {
+    uint16_t* order = (uint16_t*)sm.bitbuf;                 // 256 x u16   symbols sorted by count ascending
+    uint32_t* weight = (uint32_t*)(sm.bitbuf + 512);        // 511 x u32
+    uint16_t* parent = (uint16_t*)(sm.bitbuf + 512 + 2048); // 511 x u16
+    uint8_t* depth = sm.bitbuf + 512 + 2048 + 1024;         // 511 x u8
+    int n = 0;
+    for (int s0 = 0; s0 < 256; s0 += 32) n += __popc(__ballot_sync(0xFFFFFFFFu, sm.hist[s0 + lane] != 0));
     if (n < 2) return 0;
-    for (int i = 1; i < n; i++) {
-        uint16_t v = order[i]; uint32_t c = sm.hist[v]; int j = i - 1;
-        while (j >= 0 && sm.hist[order[j]] > c) { order[j + 1] = order[j]; j--; }
-        order[j + 1] = v;
+    for (int s = lane; s < 256; s += 32) {
+        const uint32_t c = sm.hist[s];
+        if (!c) continue;
+        int rank = 0;
+        for (int j = 0; j < 256; j++) { const uint32_t cj = sm.hist[j]; rank += (cj != 0) && (cj < c || (cj == c && j < s)); }
+        order[rank] = (uint16_t)s;
     }
-    // two-queue Huffman: leaves 0..n-1 (sorted), internal nodes n..2n-2
-    uint32_t weight[511]; uint16_t parent[511];
-    for (int i = 0; i < n; i++) weight[i] = sm.hist[order[i]];
-    int leaf = 0, inode = n, next = n;
-    for (int k = 0; k < n - 1; k++) {
-        int a, b;
-        if (leaf < n && (inode >= next || weight[leaf] <= weight[inode])) a = leaf++; else a = inode++;
-        if (leaf < n && (inode >= next || weight[leaf] <= weight[inode])) b = leaf++; else b = inode++;
-        weight[next] = weight[a] + weight[b]; parent[a] = (uint16_t)next; parent[b] = (uint16_t)next; next++;
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < n; i++) weight[i] = sm.hist[order[i]];
+        int leaf = 0, inode = n, next = n;
+        for (int k = 0; k < n - 1; k++) {       // two-queue Huffman: leaves 0..n-1 (sorted), internal nodes n..2n-2
+            int a, b;
+            if (leaf < n && (inode >= next || weight[leaf] <= weight[inode])) a = leaf++; else a = inode++;
+            if (leaf < n && (inode >= next || weight[leaf] <= weight[inode])) b = leaf++; else b = inode++;
+            weight[next] = weight[a] + weight[b]; parent[a] = (uint16_t)next; parent[b] = (uint16_t)next; next++;
+        }
+        depth[next - 1] = 0;
+        for (int i = next - 2; i >= 0; i--) depth[i] = (uint8_t)(depth[parent[i]] + 1);
+        // histogram of code lengths, limited to 11 (miniz-style redistribution keeps the code complete)
+        const int L = 11;
+        int num[33]; for (int i = 0; i <= 32; i++) num[i] = 0;
+        for (int i = 0; i < n; i++) num[depth[i] > 32 ? 32 : depth[i]]++;
+        for (int i = L + 1; i <= 32; i++) { num[L] += num[i]; num[i] = 0; }
+        unsigned total = 0;
+        for (int i = L; i > 0; i--) total += (unsigned)num[i] << (L - i);
+        while (total != (1u << L)) {
+            num[L]--;
+            for (int i = L - 1; i > 0; i--) if (num[i]) { num[i]--; num[i + 1] += 2; break; }
+            total--;
+        }
+        // most frequent symbols (end of `order`) get the shortest codes
+        int idx = n - 1, maxlen = 0;
+        for (int l = 1; l <= L; l++) for (int k = 0; k < num[l]; k++) { sm.hlen[order[idx--]] = (uint8_t)l; maxlen = l; }
+        sm.scratch[2] = (uint32_t)maxlen;
     }
-    // depths: root = next-1
-    uint8_t depth[511];
-    depth[next - 1] = 0;
-    for (int i = next - 2; i >= 0; i--) depth[i] = (uint8_t)(depth[parent[i]] + 1);
-    // histogram of code lengths, limited to 11 (miniz-style redistribution keeps the code complete)
-    const int L = 11;
-    int num[33]; for (int i = 0; i <= 32; i++) num[i] = 0;
-    for (int i = 0; i < n; i++) num[depth[i] > 32 ? 32 : depth[i]]++;
-    for (int i = L + 1; i <= 32; i++) { num[L] += num[i]; num[i] = 0; }
-    unsigned total = 0;
-    for (int i = L; i > 0; i--) total += (unsigned)num[i] << (L - i);
-    while (total != (1u << L)) {
-        num[L]--;
-        for (int i = L - 1; i > 0; i--) if (num[i]) { num[i]--; num[i + 1] += 2; break; }
-        total--;
-    }
-    // assign lengths: most frequent symbols (end of `order`) get the shortest codes
-    int idx = n - 1, maxlen = 0;
-    for (int l = 1; l <= L; l++) for (int k = 0; k < num[l]; k++) { sm.hlen[order[idx--]] = (uint8_t)l; maxlen = l; }
-    (void)nlit;
-    return maxlen;
+    __syncwarp();
+    return (int)sm.scratch[2];
 }
 
 __global__ void __launch_bounds__(32) zk_entropy_enc_kernel(ZkEncodeArgs a) {
@@ -405,22 +412,20 @@ __global__ void __launch_bounds__(32) zk_entropy_enc_kernel(ZkEncodeArgs a) {
         __syncwarp();
         // decide: Raw / RLE / Huffman
         int maxlen = 0; uint32_t lit_mode = 0;           // 0 raw, 1 rle, 2 huffman
-        if (lane == 0) {
-            uint32_t mx = 0; for (int s = 0; s < 256; s++) if (sm.hist[s] > mx) mx = sm.hist[s];
-            if (nlit > 0 && mx == nlit && nlit >= 2) lit_mode = 1;
-            else if (nlit >= 64) {
-                maxlen = zkc_huf_build(sm, nlit);
-                if (maxlen) {
-                    unsigned long long bits = 0;
-                    for (int s = 0; s < 256; s++) bits += (unsigned long long)sm.hist[s] * sm.hlen[s];
-                    uint32_t est = (uint32_t)((bits + 7) / 8) + 8 + 130;
-                    if (est < nlit) lit_mode = 2;
-                }
+        uint32_t mx = 0;
+        for (int s = lane; s < 256; s += 32) mx = max(mx, sm.hist[s]);
+        for (int d = 16; d; d >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+        if (nlit > 0 && mx == nlit && nlit >= 2) lit_mode = 1;
+        else if (nlit >= 64) {
+            maxlen = zkc_huf_build(sm, lane);
+            if (maxlen) {
+                uint32_t bits = 0;
+                for (int s = lane; s < 256; s += 32) bits += sm.hist[s] * sm.hlen[s];
+                for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+                uint32_t est = (bits + 7) / 8 + 8 + 130;
+                if (est < nlit) lit_mode = 2;
             }
-            sm.scratch[1] = lit_mode; sm.scratch[2] = (uint32_t)maxlen;
         }
-        __syncwarp();
-        lit_mode = sm.scratch[1]; maxlen = (int)sm.scratch[2];
 
         uint32_t tree_bytes = 0;
         if (lit_mode == 2) {
@@ -470,10 +475,10 @@ __global__ void __launch_bounds__(32) zk_entropy_enc_kernel(ZkEncodeArgs a) {
                     }
                 }
                 sm.scratch[3] = tb;
-                if (!tb) sm.scratch[1] = 0;              // cannot describe the tree: raw literals
             }
             __syncwarp();
-            lit_mode = sm.scratch[1]; tree_bytes = sm.scratch[3];
+            tree_bytes = sm.scratch[3];
+            if (!tree_bytes) lit_mode = 0;               // cannot describe the tree: raw literals
         }
 
         if (lit_mode == 2) {
