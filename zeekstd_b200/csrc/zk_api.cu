@@ -152,6 +152,7 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->slot[0].stream;
     const size_t sub_bytes = zk_env_size("ZK_DEV_SUB_BYTES", (size_t)1 << 30);
     ZkDecodeWs* ws = &c->slot[0].dws;
+    ws->share = 1;
     cudaEventRecord(c->ev0, st);
     int32_t worst = 0;
     for (uint32_t first = 0; first < n;) {
@@ -180,6 +181,7 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     sb.c_rel.resize(cnt + 1); sb.d_rel.resize(cnt + 1);
     for (uint32_t j = 0; j <= cnt; j++) { sb.c_rel[j] = c_off[f + j] - c_off[f]; sb.d_rel[j] = d_off[f + j] - d_off[f]; }
     ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
+    s.dws.share = zk_host_slots();
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
     if (rc) return rc;
@@ -208,7 +210,7 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
     if (!c || (n && (!comp || !c_off || !d_off || !dst))) return ZK_ERR_INVALID_ARG;
     if (n == 0) return 0;
     ZK_RT_OK(cudaSetDevice(c->device));
-    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)256 << 20);     // measured best on B200 (tools/e2e_sweep.py)
     ZkSubDec sub[ZK_SLOTS];
     const int NS = zk_host_slots();
     int32_t worst = 0;
@@ -285,7 +287,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
     const uint32_t nf = zk_frames_of(n, frame_size);
     if (nf > frames_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
     ZK_RT_OK(cudaSetDevice(c->device));
-    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES_ENC", (size_t)64 << 20);   // measured best on B200 (tools/e2e_sweep.py)
     uint32_t per = (uint32_t)(sub_bytes / frame_size); if (per == 0) per = 1;
     // The compressed size of a sub-batch is only known when it completes, so output positions are assigned in
     // order at completion time: H2D and kernels of later sub-batches overlap the D2H of earlier ones.

@@ -1157,7 +1157,8 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     // exec stage: ring size / warps per entry chosen from how many entries share the machine
     // Each entry is one serial dependency chain, so throughput comes from entries in flight: pick warps per
     // CTA and ring size such that (if possible) every entry of the batch is resident at once.
-    int per_sm = (int)((n + (uint32_t)sms - 1) / (uint32_t)sms);
+    // (`share` > 1: that many sub-batches of a host pipeline run concurrently on different streams)
+    int per_sm = (int)(((unsigned long long)n * (unsigned)(ws->share > 0 ? ws->share : 1) + (uint32_t)sms - 1) / (uint32_t)sms);
     int W = exec_warps;
     if (W <= 0) { W = 16 / per_sm; if (W < 1) W = 1; }
     if (W > 16) W = 16;
