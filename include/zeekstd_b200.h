@@ -100,7 +100,8 @@ int32_t zk_decompress_frames(zk_ctx* ctx, const uint8_t* comp, const uint64_t* c
  * Device-resident variants (zero-copy; used for roofline measurements and multi-GPU pipelines).
  * d_* are CUDA device pointers, 16-byte aligned, with >= 16 readable bytes after the last byte;
  * offset / size arrays stay on the HOST.  cuda_stream is a cudaStream_t (NULL = the context's own
- * stream).  The call returns after the work has completed on that stream.
+ * non-blocking stream; pass cudaStreamLegacy (0x1) to order the work on the legacy default stream, e.g.
+ * after PyTorch ops).  The call returns after the work has completed on that stream.
  */
 int32_t zk_compress_frames_dev(zk_ctx* ctx, const void* d_src, size_t n, uint32_t frame_size, int32_t level,
                                int32_t checksum, void* d_dst, size_t dst_cap, uint32_t* c_sizes, uint32_t* d_sizes,

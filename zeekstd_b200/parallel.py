@@ -27,8 +27,16 @@ def frame_ranges(n_frames: int, world: int):
     return [(min(r * per, n_frames), min((r + 1) * per, n_frames)) for r in range(world)]
 
 
+def torch_stream_handle(device) -> ctypes.c_void_p:
+    """cudaStream_t of torch's current stream; torch's default stream is the legacy NULL stream, which the C ABI
+    spells cudaStreamLegacy (0x1) because NULL there means "the context's own stream"."""
+    h = torch.cuda.current_stream(device).cuda_stream
+    return ctypes.c_void_p(h if h else 1)
+
+
 class DeviceCodec:
-    """zero-copy codec over CUDA tensors (zk_*_frames_dev)"""
+    """zero-copy codec over CUDA tensors (zk_*_frames_dev).  The kernels are enqueued on torch's CURRENT stream so they
+    are ordered after the tensor ops / NCCL receives that produced their inputs."""
 
     def __init__(self, ctx):
         self.ctx, self.lib = ctx, ctx.lib
@@ -43,7 +51,7 @@ class DeviceCodec:
         nf = ctypes.c_uint32(); dl = ctypes.c_size_t()
         rc = self.lib.zk_compress_frames_dev(self.ctx._h, src.data_ptr(), n, frame_size, level, int(checksum), dst.data_ptr(), cap,
                                              cs.ctypes.data_as(_native.u32p), ds.ctypes.data_as(_native.u32p), nfmax, ctypes.byref(nf),
-                                             ctypes.byref(dl), None)
+                                             ctypes.byref(dl), torch_stream_handle(x.device))
         if rc:
             raise RuntimeError(f"zk_compress_frames_dev: {rc}")
         return dst[: dl.value], cs[: nf.value].astype(np.int64), ds[: nf.value].astype(np.int64)
@@ -54,7 +62,7 @@ class DeviceCodec:
         src = torch.cat([comp, torch.zeros(64, dtype=torch.uint8, device=comp.device)])
         out = torch.empty(int(do[-1]) + 64, dtype=torch.uint8, device=comp.device)
         rc = self.lib.zk_decompress_frames_dev(self.ctx._h, src.data_ptr(), co.ctypes.data_as(_native.u64p), do.ctypes.data_as(_native.u64p), n,
-                                               out.data_ptr(), int(verify), None, None)
+                                               out.data_ptr(), int(verify), None, torch_stream_handle(comp.device))
         if rc:
             raise RuntimeError(f"zk_decompress_frames_dev: {rc}")
         return out[: int(do[-1])]
