@@ -8,8 +8,8 @@
 //
 //   K-C1 zk_match_kernel     one warp / block : LZ77 match finding (hash table in shared memory),
 //                                               greedy parse resolved with ballots, sequence + literal emit
-//   K-C2 zk_entropy_enc_kernel one warp / block : Huffman literals (4 streams, warp-scan bit packing) +
-//                                               FSE sequences (normalise, table build, backward bitstream)
+//   K-C2s zk_seq_enc_kernel  one LANE / block : FSE sequences (repeat offsets, normalise, table build, backward bitstream)
+//   K-C2l zk_lit_enc_kernel  one warp / block : Huffman literals (4 streams, warp-scan bit packing) + block assembly
 //   K-C3 zk_frame_layout_kernel / zk_frame_gather_kernel : frame headers, block gather, optional XXH64
 //
 // Output is a standard Zstandard frame per seek-table entry (RFC 8878), decodable
@@ -26,9 +26,12 @@
 
 struct ZkcBlock {                        // per-block record in HBM
     uint32_t nseq, nlit;                 // K-C1
-    uint32_t csize;                      // K-C2: size of the staged block incl. its 3-byte header
+    uint32_t seq_hdr, seq_bits;          // K-C2s: bytes of the sequence-section header / bitstream (seq_hdr == 0: not encodable)
+    uint32_t csize;                      // K-C2l: size of the staged block incl. its 3-byte header
     uint32_t out_off;                    // K-C3: offset of the block inside its frame
 };
+#define ZKC_SEQSEC 16384u                // per-block scratch for the sequence section: [0,256) header, [256,..) bitstream
+#define ZKC_SEQHDR 256u
 
 struct ZkEncodeArgs {
     const uint8_t* src; size_t n; uint32_t frame_size; uint32_t n_frames; uint32_t blocks_per_frame; uint32_t n_blocks;
@@ -37,6 +40,7 @@ struct ZkEncodeArgs {
     uint16_t* seq_ll; uint16_t* seq_ml; uint32_t* seq_off;      // ZKC_MAXSEQ per block
     uint8_t* lits;                                              // ZKC_BLOCK per block
     uint8_t* stage;                                             // ZKC_SLOT per block
+    uint8_t* seqsec;                                            // ZKC_SEQSEC per block
     uint32_t* frame_csize; unsigned long long* frame_off; uint32_t* frame_hash;
     uint8_t* dst; size_t dst_cap; unsigned long long* total; uint32_t* error;
 };
@@ -99,8 +103,11 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         }
         size_t ip = lo, anchor = lo;
         uint32_t rep = 0;                                   // last emitted offset (0 = none)
+        uint32_t misses = 0;                                // consecutive windows without a match: widen the stride (incompressible data)
         while (ip < mflimit) {
-            const size_t p = ip + lane;
+            const uint32_t stride = 1u + min(misses >> 3, 3u);
+            const size_t wb = ip;
+            const size_t p = wb + (size_t)lane * stride;
             const bool valid = p < mflimit;
             unsigned long long cur = 0; uint32_t h = 0, cand = 0;
             if (valid) { cur = zkc_ld8(src + p); h = zkc_hash5(cur); cand = table[h]; }
@@ -125,29 +132,44 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
                 }
             }
             const uint32_t found = __ballot_sync(0xFFFFFFFFu, mlen0 != 0);
-            if (!found) { ip += 32; continue; }
-            const int f = __ffs((int)found) - 1;
-            const uint32_t off = __shfl_sync(0xFFFFFFFFu, moff, f);
-            uint32_t ml = __shfl_sync(0xFFFFFFFFu, mlen0, f);
-            const size_t mpos = ip + f;
-            if (ml == 8) {
-                // extend cooperatively: lane k compares bytes [8 + 8k, 16 + 8k) of the match, 256 bytes a round
-                for (;;) {
-                    const size_t q = mpos + ml + (size_t)lane * 8;
-                    uint32_t eq = 8;
-                    if (q + 8 <= hi) { unsigned long long x = zkc_ld8(src + q) ^ zkc_ld8(src + q - off); if (x) eq = (uint32_t)(__ffsll((long long)x) - 1) >> 3; }
-                    else { eq = 0; for (size_t t = q; t < hi && src[t] == src[t - off]; t++) eq++; }
-                    const uint32_t stop = __ballot_sync(0xFFFFFFFFu, eq < 8);
-                    if (stop) { const int g = __ffs((int)stop) - 1; ml += 8 * g + __shfl_sync(0xFFFFFFFFu, eq, g); break; }
-                    ml += 256;
+            if (!found) { ip = wb + 32u * stride; misses++; continue; }
+            misses = 0;
+            // take every non-overlapping match of this window, left to right (one memory round trip serves them all)
+            uint32_t next_lane = 0;
+            while (next_lane < 32) {
+                const uint32_t m = found & (0xFFFFFFFFu << next_lane);
+                if (!m) break;
+                int f = __ffs((int)m) - 1;
+                uint32_t ml = __shfl_sync(0xFFFFFFFFu, mlen0, f);
+                // one step of lazy matching: a clearly longer match starting at the next position wins (one more literal)
+                if (a.level >= 2 && ml < 8 && f < 31 && ((found >> (f + 1)) & 1u)) {
+                    const uint32_t ml2 = __shfl_sync(0xFFFFFFFFu, mlen0, f + 1);
+                    if (ml2 > ml + 1) { f++; ml = ml2; }
                 }
+                const uint32_t off = __shfl_sync(0xFFFFFFFFu, moff, f);
+                const size_t mpos = wb + (size_t)f * stride;
+                if (ml == 8) {
+                    // extend cooperatively: lane k compares bytes [8 + 8k, 16 + 8k) of the match, 256 bytes a round
+                    for (;;) {
+                        const size_t q = mpos + ml + (size_t)lane * 8;
+                        uint32_t eq = 8;
+                        if (q + 8 <= hi) { unsigned long long x = zkc_ld8(src + q) ^ zkc_ld8(src + q - off); if (x) eq = (uint32_t)(__ffsll((long long)x) - 1) >> 3; }
+                        else { eq = 0; for (size_t t = q; t < hi && src[t] == src[t - off]; t++) eq++; }
+                        const uint32_t stop = __ballot_sync(0xFFFFFFFFu, eq < 8);
+                        if (stop) { const int g = __ffs((int)stop) - 1; ml += 8 * g + __shfl_sync(0xFFFFFFFFu, eq, g); break; }
+                        ml += 256;
+                    }
+                }
+                // emit: literals [anchor, mpos) then the match
+                const uint32_t ll = (uint32_t)(mpos - anchor);
+                for (uint32_t i = lane; i < ll; i += 32) o_lit[nlit + i] = src[anchor + i];
+                if (lane == 0) { o_ll[nseq] = (uint16_t)ll; o_ml[nseq] = (uint16_t)(ml - 3); o_off[nseq] = off; }
+                nlit += ll; nseq++;
+                anchor = mpos + ml; rep = off;
+                const size_t rel = anchor - wb;
+                next_lane = rel >= 32u * stride ? 32u : (uint32_t)((rel + stride - 1) / stride);
             }
-            // emit: literals [anchor, mpos) then the match
-            const uint32_t ll = (uint32_t)(mpos - anchor);
-            for (uint32_t i = lane; i < ll; i += 32) o_lit[nlit + i] = src[anchor + i];
-            if (lane == 0) { o_ll[nseq] = (uint16_t)ll; o_ml[nseq] = (uint16_t)(ml - 3); o_off[nseq] = off; }
-            nlit += ll; nseq++;
-            ip = mpos + ml; anchor = ip; rep = off;
+            ip = anchor > wb + 32u * stride ? anchor : wb + 32u * stride;
         }
         const uint32_t rest = (uint32_t)(hi - anchor);
         for (uint32_t i = lane; i < rest; i += 32) o_lit[nlit + i] = src[anchor + i];
@@ -171,30 +193,32 @@ __constant__ uint8_t ZKC_ML_CODE[128] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,1
 __device__ __forceinline__ uint32_t zkc_ll_code(uint32_t ll) { return ll < 64 ? ZKC_LL_CODE[ll] : (uint32_t)zk_highbit(ll) + 19; }
 __device__ __forceinline__ uint32_t zkc_ml_code(uint32_t mlb) { return mlb < 128 ? ZKC_ML_CODE[mlb] : (uint32_t)zk_highbit(mlb) + 36; }
 
-// forward bit writer into shared memory (A.7 streams are written forward, read backward)
-struct ZkcBitW {
+// forward bit writer (A.7 streams are written forward, read backward).  WORDS: the base is 4-byte aligned and full
+// 32-bit words are stored at once (used when a lane streams straight into HBM).
+template <bool WORDS>
+struct ZkcBitWT {
     uint8_t* p; uint32_t cap, pos; unsigned long long acc; int nb; bool ovf;
     __device__ __forceinline__ void init(uint8_t* buf, uint32_t capacity) { p = buf; cap = capacity; pos = 0; acc = 0; nb = 0; ovf = false; }
     __device__ __forceinline__ void add(uint32_t v, int n) {          // n <= 32
         acc |= (unsigned long long)(v & (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u))) << nb; nb += n;
         if (nb >= 32) {
-            if (pos + 4 <= cap) { p[pos] = (uint8_t)acc; p[pos + 1] = (uint8_t)(acc >> 8); p[pos + 2] = (uint8_t)(acc >> 16); p[pos + 3] = (uint8_t)(acc >> 24); }
-            else ovf = true;
+            if (pos + 4 <= cap) {
+                if (WORDS) *(uint32_t*)(p + pos) = (uint32_t)acc;
+                else { p[pos] = (uint8_t)acc; p[pos + 1] = (uint8_t)(acc >> 8); p[pos + 2] = (uint8_t)(acc >> 16); p[pos + 3] = (uint8_t)(acc >> 24); }
+            } else ovf = true;
             pos += 4; acc >>= 32; nb -= 32;
         }
     }
     // end mark + flush; returns total bytes or 0 on overflow
-    __device__ __forceinline__ uint32_t finish() {
-        add(1, 1);
-        while (nb > 0) { if (pos < cap) p[pos] = (uint8_t)acc; else ovf = true; pos++; acc >>= 8; nb -= 8; }
-        return ovf ? 0 : pos;
-    }
+    __device__ __forceinline__ uint32_t finish() { add(1, 1); return finish_raw(); }
     // flush without end mark (FSE table descriptions, A.6)
     __device__ __forceinline__ uint32_t finish_raw() {
         while (nb > 0) { if (pos < cap) p[pos] = (uint8_t)acc; else ovf = true; pos++; acc >>= 8; nb -= 8; }
         return ovf ? 0 : pos;
     }
 };
+typedef ZkcBitWT<false> ZkcBitW;
+typedef ZkcBitWT<true> ZkcBitWW;
 
 // FSE compression table for one symbol alphabet (state values in [S, 2S))
 struct ZkcFse {
@@ -295,13 +319,15 @@ __device__ __forceinline__ void zkc_fse_init_state(const ZkcFse& t, uint32_t sym
     const uint32_t value = (nb_out << 16) - dnb;
     state = t.state_tbl[(value >> nb_out) + t.delta_find[sym]];
 }
-__device__ __forceinline__ void zkc_fse_encode(const ZkcFse& t, ZkcBitW& w, uint32_t sym, uint32_t& state) {
+template <class W>
+__device__ __forceinline__ void zkc_fse_encode(const ZkcFse& t, W& w, uint32_t sym, uint32_t& state) {
     if (t.mode == 1) return;
     const uint32_t nb_out = (state + t.delta_nb[sym]) >> 16;
     w.add(state, (int)nb_out);
     state = t.state_tbl[(state >> nb_out) + t.delta_find[sym]];
 }
-__device__ __forceinline__ void zkc_fse_flush(const ZkcFse& t, ZkcBitW& w, uint32_t state) {
+template <class W>
+__device__ __forceinline__ void zkc_fse_flush(const ZkcFse& t, W& w, uint32_t state) {
     if (t.mode == 1) return;
     w.add(state, t.log);
 }
@@ -313,14 +339,128 @@ __device__ void zkc_fse_set_predefined(ZkcFse& t, int which) {
     t.mode = 0;
 }
 
+// =============================================================================================
+// K-C2s: sequence section -- one LANE per block.
+// Coding the sequences of a block is a serial chain (repeat-offset history, FSE state machine), so the parallel axis
+// is the block: every lane runs the same code over ITS block with ITS tables in shared memory.  The section is
+// written to a per-block scratch ([0,256) header + table descriptions, [256,..) bitstream) and moved into place by
+// the literal/assembly kernel.
+// =============================================================================================
+#define ZKC_SEQ_LANES 16
+struct ZkcSeqSlot { ZkcFse fse[3]; uint32_t cnt[3][64]; uint8_t symof[512]; };
+struct ZkcTabs { uint32_t ll_base[36], ml_base[53]; uint8_t ll_bits[36], ml_bits[53], ll_code[64], ml_code[128]; };
+__device__ __forceinline__ uint32_t zkc_llc(const ZkcTabs& tb, uint32_t ll) { return ll < 64 ? tb.ll_code[ll] : (uint32_t)zk_highbit(ll) + 19; }
+__device__ __forceinline__ uint32_t zkc_mlc(const ZkcTabs& tb, uint32_t mlb) { return mlb < 128 ? tb.ml_code[mlb] : (uint32_t)zk_highbit(mlb) + 36; }
+
+// returns false if the section cannot be encoded within the scratch (the block then becomes a Raw block)
+__device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const uint16_t* s_ll, const uint16_t* s_ml, uint32_t* s_off, uint32_t nseq,
+                                     bool first_block, uint8_t* out, uint32_t* hdr_bytes, uint32_t* bits_bytes) {
+    // repeat-offset substitution (serial history, A.5) turns s_off into Offset_Value in place.  Blocks are coded
+    // independently, so repeat codes are used only once three explicit offsets have been coded in this block (the
+    // decoder's history is then certain); the first block of a frame starts from the known {1,4,8}.
+    {
+        uint32_t r0 = 1, r1 = 4, r2 = 8, known = first_block ? 3 : 0;
+        for (uint32_t i = 0; i < nseq; i++) {
+            const uint32_t off = s_off[i], ll = s_ll[i];
+            uint32_t ov = off + 3;
+            if (known == 3) {
+                if (ll != 0) { if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3; }
+                else { if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3; }
+            }
+            if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
+            else {
+                uint32_t idx = ov - 1 + (ll == 0);
+                if (idx == 1) { uint32_t t = r1; r1 = r0; r0 = t; }
+                else if (idx == 2) { uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
+                else if (idx == 3) { uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
+            }
+            s_off[i] = ov;
+        }
+    }
+    for (int i = 0; i < 3 * 64; i++) (&sl.cnt[0][0])[i] = 0;
+    for (uint32_t i = 0; i < nseq; i++) { sl.cnt[0][zkc_llc(tb, s_ll[i])]++; sl.cnt[1][zk_highbit(s_off[i])]++; sl.cnt[2][zkc_mlc(tb, s_ml[i])]++; }
+    uint32_t hp = 0;
+    if (nseq < 128) out[hp++] = (uint8_t)nseq;
+    else if (nseq < 0x7F00) { out[hp++] = (uint8_t)((nseq >> 8) + 128); out[hp++] = (uint8_t)nseq; }
+    else { out[hp++] = 255; out[hp++] = (uint8_t)(nseq - 0x7F00); out[hp++] = (uint8_t)((nseq - 0x7F00) >> 8); }
+    const uint32_t modes_at = hp++;
+    uint32_t modes = 0;
+    for (int t = 0; t < 3; t++) {
+        ZkcFse& ft = sl.fse[t];
+        const int max_log = t == 1 ? 8 : 9, nsym_all = t == 0 ? 36 : (t == 1 ? 32 : 53);
+        int last = nsym_all - 1; while (last > 0 && sl.cnt[t][last] == 0) last--;
+        uint32_t distinct = 0; for (int q = 0; q <= last; q++) distinct += sl.cnt[t][q] != 0;
+        if (distinct == 1) { ft.mode = 1; ft.rle_sym = (uint32_t)last; ft.log = 0; out[hp++] = (uint8_t)last; modes |= 1u << (6 - 2 * t); }
+        else if (nseq < 48 && (t != 1 || last <= 28)) { zkc_fse_set_predefined(ft, t); zkc_fse_build(ft, sl.symof); }
+        else {
+            int lg = zk_highbit(nseq) - 1; if (lg < 5) lg = 5; if (lg > max_log) lg = max_log;
+            int need = zk_highbit(distinct) + 1; if (lg < need) lg = need; if (lg > max_log) return false;
+            zkc_fse_normalize(ft, sl.cnt[t], last + 1, nseq, lg);
+            ft.mode = 2;
+            zkc_fse_build(ft, sl.symof);
+            uint32_t hb = zkc_fse_write_ncount(ft, out + hp, ZKC_SEQHDR - 6 - hp);
+            if (!hb) return false;
+            hp += hb; modes |= 2u << (6 - 2 * t);
+        }
+    }
+    out[modes_at] = (uint8_t)modes;
+    // backward bitstream: last sequence first (mirror of the decoder's order, A.5)
+    ZkcBitWW w; w.init(out + ZKC_SEQHDR, ZKC_SEQSEC - ZKC_SEQHDR);
+    uint32_t st_ll, st_of, st_ml;
+    uint32_t i = nseq - 1;
+    uint32_t llv = s_ll[i], mlb = s_ml[i], ov = s_off[i];
+    uint32_t llc = zkc_llc(tb, llv), mlc = zkc_mlc(tb, mlb), ofc = (uint32_t)zk_highbit(ov);
+    zkc_fse_init_state(sl.fse[2], mlc, st_ml); zkc_fse_init_state(sl.fse[1], ofc, st_of); zkc_fse_init_state(sl.fse[0], llc, st_ll);
+    w.add(llv - tb.ll_base[llc], tb.ll_bits[llc]);
+    w.add(mlb + 3 - tb.ml_base[mlc], tb.ml_bits[mlc]);
+    w.add(ov - (1u << ofc), (int)ofc);
+    while (i-- > 0) {
+        llv = s_ll[i]; mlb = s_ml[i]; ov = s_off[i];
+        llc = zkc_llc(tb, llv); mlc = zkc_mlc(tb, mlb); ofc = (uint32_t)zk_highbit(ov);
+        zkc_fse_encode(sl.fse[1], w, ofc, st_of);
+        zkc_fse_encode(sl.fse[2], w, mlc, st_ml);
+        zkc_fse_encode(sl.fse[0], w, llc, st_ll);
+        w.add(llv - tb.ll_base[llc], tb.ll_bits[llc]);
+        w.add(mlb + 3 - tb.ml_base[mlc], tb.ml_bits[mlc]);
+        w.add(ov - (1u << ofc), (int)ofc);
+    }
+    zkc_fse_flush(sl.fse[2], w, st_ml); zkc_fse_flush(sl.fse[1], w, st_of); zkc_fse_flush(sl.fse[0], w, st_ll);
+    const uint32_t sb = w.finish();
+    if (!sb) return false;
+    *hdr_bytes = hp; *bits_bytes = sb;
+    return true;
+}
+
+__global__ void __launch_bounds__(32) zk_seq_enc_kernel(ZkEncodeArgs a) {
+    ZK_DYN_SMEM(smem);
+    ZkcTabs* tb = (ZkcTabs*)smem;
+    ZkcSeqSlot* slots = (ZkcSeqSlot*)(smem + ((sizeof(ZkcTabs) + 15) & ~(size_t)15));
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 36; i += 32) { tb->ll_base[i] = ZK_LL_BASE[i]; tb->ll_bits[i] = ZK_LL_BITS[i]; }
+    for (int i = lane; i < 53; i += 32) { tb->ml_base[i] = ZK_ML_BASE[i]; tb->ml_bits[i] = ZK_ML_BITS[i]; }
+    for (int i = lane; i < 64; i += 32) tb->ll_code[i] = ZKC_LL_CODE[i];
+    for (int i = lane; i < 128; i += 32) tb->ml_code[i] = ZKC_ML_CODE[i];
+    __syncwarp();
+    const uint32_t b = blockIdx.x * ZKC_SEQ_LANES + lane;
+    if (lane < ZKC_SEQ_LANES && b < a.n_blocks) {
+        const uint32_t nseq = a.blocks[b].nseq;
+        uint32_t hb = 0, sb = 0;
+        if (nseq) {
+            const bool ok = zkc_encode_sequences(slots[lane], *tb, a.seq_ll + (size_t)b * ZKC_MAXSEQ, a.seq_ml + (size_t)b * ZKC_MAXSEQ,
+                                                 a.seq_off + (size_t)b * ZKC_MAXSEQ, nseq, b % a.blocks_per_frame == 0, a.seqsec + (size_t)b * ZKC_SEQSEC, &hb, &sb);
+            if (!ok) { hb = 0; sb = 0; }
+        }
+        a.blocks[b].seq_hdr = hb; a.blocks[b].seq_bits = sb;
+    }
+}
+
 #define ZKC_BITBUF 12288u               // shared-memory bit buffer: one Huffman stream (<= 8192 symbols x 11 bits) or the sequence bitstream
 
 struct ZkcC2Smem {
     uint32_t hist[256];
     uint16_t hcode[256]; uint8_t hlen[256];
     uint8_t bitbuf[ZKC_BITBUF];
-    ZkcFse fse[3];
-    uint32_t cnt[3][64];
+    ZkcFse fse[1];                      // FSE table for the Huffman weights
     uint8_t symof[512];
     uint8_t hdr[256];                   // literal header + tree description / sequence section header + table descriptions
     uint8_t weights[256];
@@ -378,7 +518,7 @@ __device__ int zkc_huf_build(ZkcC2Smem& sm, int lane) {
     return (int)sm.scratch[2];
 }
 
-__global__ void __launch_bounds__(32) zk_entropy_enc_kernel(ZkEncodeArgs a) {
+__global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
     __shared__ ZkcC2Smem sm;
     const int lane = threadIdx.x;
     const uint32_t b = blockIdx.x;
@@ -564,112 +704,17 @@ __global__ void __launch_bounds__(32) zk_entropy_enc_kernel(ZkEncodeArgs a) {
         }
     }
 
-    // ------------------------------------------------------------------ sequences section (A.5)
+    // ------------------------------------------------------------------ sequences section (A.5): coded by K-C2s, moved into place here
     if (!raw_block) {
-        const uint16_t* s_ll = a.seq_ll + (size_t)b * ZKC_MAXSEQ; const uint16_t* s_ml = a.seq_ml + (size_t)b * ZKC_MAXSEQ;
-        uint32_t* s_off = a.seq_off + (size_t)b * ZKC_MAXSEQ;
         if (nseq == 0) { if (lane == 0) out[opos] = 0; opos += 1; }
         else {
-            // repeat-offset substitution (serial history, A.5) turns s_off into Offset_Value in place
-            if (lane == 0) {
-                uint32_t r0 = 1, r1 = 4, r2 = 8;
-                // history restarts per FRAME, not per block: replay is avoided by resetting only at the first block
-                // of a frame; later blocks start from the state stored by their predecessor -- blocks are coded
-                // independently here, so we conservatively never use repeat codes across the block boundary:
-                // the first three offsets of a block are always coded explicitly, which is exact iff the
-                // decoder's history equals ours afterwards.  That holds because explicit offsets overwrite it.
-                uint32_t known = k_in_frame == 0 ? 3 : 0;       // how many history slots are certain
-                for (uint32_t i = 0; i < nseq; i++) {
-                    const uint32_t off = s_off[i], ll = s_ll[i];
-                    uint32_t ov = off + 3;
-                    if (known == 3) {
-                        if (ll != 0) {
-                            if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3;
-                        } else {
-                            if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3;
-                        }
-                    }
-                    // update history exactly like the decoder will
-                    if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
-                    else {
-                        uint32_t idx = ov - 1 + (ll == 0);
-                        if (idx == 1) { uint32_t t = r1; r1 = r0; r0 = t; }
-                        else if (idx == 2) { uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
-                        else if (idx == 3) { uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
-                    }
-                    s_off[i] = ov;
-                }
-            }
-            __syncwarp();
-            // histograms of the three code alphabets
-            for (int i = lane; i < 3 * 64; i += 32) (&sm.cnt[0][0])[i] = 0;
-            __syncwarp();
-            for (uint32_t i = lane; i < nseq; i += 32) {
-                atomicAdd(&sm.cnt[0][zkc_ll_code(s_ll[i])], 1u);
-                atomicAdd(&sm.cnt[1][zk_highbit(s_off[i])], 1u);
-                atomicAdd(&sm.cnt[2][zkc_ml_code(s_ml[i])], 1u);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                uint32_t hp = 0;
-                if (nseq < 128) sm.hdr[hp++] = (uint8_t)nseq;
-                else if (nseq < 0x7F00) { sm.hdr[hp++] = (uint8_t)((nseq >> 8) + 128); sm.hdr[hp++] = (uint8_t)nseq; }
-                else { sm.hdr[hp++] = 255; sm.hdr[hp++] = (uint8_t)(nseq - 0x7F00); sm.hdr[hp++] = (uint8_t)((nseq - 0x7F00) >> 8); }
-                const uint32_t modes_at = hp++;
-                uint32_t modes = 0;
-                const int max_log[3] = {9, 8, 9}, nsym_all[3] = {36, 32, 53};
-                bool fail = false;
-                for (int t = 0; t < 3 && !fail; t++) {
-                    ZkcFse& ft = sm.fse[t];
-                    int last = nsym_all[t] - 1; while (last > 0 && sm.cnt[t][last] == 0) last--;
-                    uint32_t distinct = 0; for (int s = 0; s <= last; s++) distinct += sm.cnt[t][s] != 0;
-                    if (distinct == 1) { ft.mode = 1; ft.rle_sym = (uint32_t)last; ft.log = 0; sm.hdr[hp++] = (uint8_t)last; modes |= 1u << (6 - 2 * t); }
-                    else if (nseq < 48 && (t != 1 || last <= 28)) { zkc_fse_set_predefined(ft, t); zkc_fse_build(ft, sm.symof); }
-                    else {
-                        int lg = zk_highbit(nseq) - 1; if (lg < 5) lg = 5; if (lg > max_log[t]) lg = max_log[t];
-                        int need = zk_highbit(distinct) + 1; if (lg < need) lg = need; if (lg > max_log[t]) { fail = true; break; }
-                        zkc_fse_normalize(ft, sm.cnt[t], last + 1, nseq, lg);
-                        ft.mode = 2;
-                        zkc_fse_build(ft, sm.symof);
-                        uint32_t hb = zkc_fse_write_ncount(ft, sm.hdr + hp, 250 - hp);
-                        if (!hb) { fail = true; break; }
-                        hp += hb; modes |= 2u << (6 - 2 * t);
-                    }
-                }
-                sm.hdr[modes_at] = (uint8_t)modes;
-                sm.scratch[4] = fail ? 0 : hp;
-                if (!fail) {
-                    // backward bitstream: last sequence first (mirror of the decoder's order, A.5)
-                    ZkcBitW w; w.init(sm.bitbuf, ZKC_BITBUF);
-                    uint32_t st_ll, st_of, st_ml;
-                    uint32_t i = nseq - 1;
-                    uint32_t llv = s_ll[i], mlb = s_ml[i], ov = s_off[i];
-                    uint32_t llc = zkc_ll_code(llv), mlc = zkc_ml_code(mlb), ofc = (uint32_t)zk_highbit(ov);
-                    zkc_fse_init_state(sm.fse[2], mlc, st_ml); zkc_fse_init_state(sm.fse[1], ofc, st_of); zkc_fse_init_state(sm.fse[0], llc, st_ll);
-                    w.add(llv - ZK_LL_BASE[llc], ZK_LL_BITS[llc]);
-                    w.add(mlb + 3 - ZK_ML_BASE[mlc], ZK_ML_BITS[mlc]);
-                    w.add(ov - (1u << ofc), (int)ofc);
-                    while (i-- > 0) {
-                        llv = s_ll[i]; mlb = s_ml[i]; ov = s_off[i];
-                        llc = zkc_ll_code(llv); mlc = zkc_ml_code(mlb); ofc = (uint32_t)zk_highbit(ov);
-                        zkc_fse_encode(sm.fse[1], w, ofc, st_of);
-                        zkc_fse_encode(sm.fse[2], w, mlc, st_ml);
-                        zkc_fse_encode(sm.fse[0], w, llc, st_ll);
-                        w.add(llv - ZK_LL_BASE[llc], ZK_LL_BITS[llc]);
-                        w.add(mlb + 3 - ZK_ML_BASE[mlc], ZK_ML_BITS[mlc]);
-                        w.add(ov - (1u << ofc), (int)ofc);
-                    }
-                    zkc_fse_flush(sm.fse[2], w, st_ml); zkc_fse_flush(sm.fse[1], w, st_of); zkc_fse_flush(sm.fse[0], w, st_ll);
-                    sm.scratch[5] = w.finish();
-                }
-            }
-            __syncwarp();
-            const uint32_t hp = sm.scratch[4], sb = hp ? sm.scratch[5] : 0;
-            if (!hp || !sb || opos + hp + sb >= len + 3) raw_block = true;
+            const uint32_t hp = a.blocks[b].seq_hdr, sb = a.blocks[b].seq_bits;
+            if (!hp || opos + hp + sb >= len + 3) raw_block = true;
             else {
-                for (uint32_t i = lane; i < hp; i += 32) out[opos + i] = sm.hdr[i];
+                const uint8_t* sec = a.seqsec + (size_t)b * ZKC_SEQSEC;
+                for (uint32_t i = lane; i < hp; i += 32) out[opos + i] = sec[i];
                 opos += hp;
-                for (uint32_t i = lane; i < sb; i += 32) out[opos + i] = sm.bitbuf[i];
+                for (uint32_t i = lane; i < sb; i += 32) out[opos + i] = sec[ZKC_SEQHDR + i];
                 opos += sb;
             }
         }
@@ -860,6 +905,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     const size_t o_off = off; off = zkc_align(off + n_blocks * ZKC_MAXSEQ * 4);
     const size_t o_lits = off; off = zkc_align(off + n_blocks * ZKC_BLOCK);
     const size_t o_stage = off; off = zkc_align(off + n_blocks * ZKC_SLOT + 64);
+    const size_t o_seqsec = off; off = zkc_align(off + n_blocks * ZKC_SEQSEC);
     const size_t o_fcs = off; off = zkc_align(off + (size_t)n_frames * 4);
     const size_t o_foff = off; off = zkc_align(off + (size_t)n_frames * 8);
     const size_t o_fh = off; off = zkc_align(off + (size_t)n_frames * 4);
@@ -884,15 +930,18 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     a.level = level <= 0 ? 3 : level; a.checksum = checksum ? 1 : 0;
     a.blocks = (ZkcBlock*)(base + o_blocks);
     a.seq_ll = (uint16_t*)(base + o_ll); a.seq_ml = (uint16_t*)(base + o_ml); a.seq_off = (uint32_t*)(base + o_off);
-    a.lits = base + o_lits; a.stage = base + o_stage;
+    a.lits = base + o_lits; a.stage = base + o_stage; a.seqsec = base + o_seqsec;
     a.frame_csize = (uint32_t*)(base + o_fcs); a.frame_off = (unsigned long long*)(base + o_foff); a.frame_hash = (uint32_t*)(base + o_fh);
     a.dst = d_dst; a.dst_cap = dst_cap; a.total = (unsigned long long*)(base + o_tot); a.error = (uint32_t*)(base + o_tot + 8);
     ZKC_CUDA_OK(cudaMemsetAsync(base + o_tot, 0, 16, stream));
     ws->prof.begin(5, stream);
     ZK_LAUNCH(zk_match_kernel, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
     ws->prof.end(5, stream);
+    const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqSlot) * ZKC_SEQ_LANES;
+    if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
     ws->prof.begin(6, stream);
-    ZK_LAUNCH(zk_entropy_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
+    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SEQ_LANES - 1) / ZKC_SEQ_LANES), 32, seq_smem, stream, a);
+    ZK_LAUNCH(zk_lit_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
     ws->prof.end(6, stream);
     ws->prof.begin(7, stream);
     if (checksum) ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, stream, a);
@@ -902,7 +951,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ws->prof.end(7, stream);
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes, a.frame_csize, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, stream));
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes + ws->cap_frames, a.total, 16, cudaMemcpyDeviceToHost, stream));
-    ws->launches += 5 + (checksum ? 1 : 0);
+    ws->launches += 6 + (checksum ? 1 : 0);
     ws->pending_frames = n_frames;
     return 0;
 }

@@ -8,6 +8,7 @@ struct ZkEncodeWs {                    // HBM scratch owned by a zk_ctx slot, gr
     int sm_count = 0;
     unsigned long long launches = 0;
     uint32_t pending_frames = 0;
+    bool attr_set = false;
     ZkProf prof;
 };
 
