@@ -20,14 +20,15 @@
 #define ZKC_BLOCK 32768u                 // zstd block size used by this encoder (<= Block_Maximum_Size)
 #define ZKC_HLOG 12                      // hash table: 4096 x u16 per warp
 #define ZKC_MINMATCH 5
-#define ZKC_MAXSEQ (ZKC_BLOCK / 4 + 1)   // every sequence covers at least 4 bytes (repeat matches may be 4 long)
+#define ZKC_MAXSEQ (ZKC_BLOCK / 4 + 8)   // every sequence covers at least 4 bytes (repeat matches may be 4 long); multiple of 8 for 16-byte chunked loads
 #define ZKC_SLOT (ZKC_BLOCK + 64u)       // per-block staging slot for the compressed block
 #define ZKC_FRAME_HDR 10u                // magic + FHD + window descriptor + 4-byte FCS
 
 struct ZkcBlock {                        // per-block record in HBM
     uint32_t nseq, nlit;                 // K-C1
     uint32_t seq_hdr, seq_bits;          // K-C2s: bytes of the sequence-section header / bitstream (seq_hdr == 0: not encodable)
-    uint32_t csize;                      // K-C2l: size of the staged block incl. its 3-byte header
+    uint32_t lit_bytes, last_flag;       // K-C2l: bytes staged so far (3-byte header gap + literals section; 0 = send the block Raw)
+    uint32_t csize;                      // K-C2f: size of the staged block incl. its 3-byte header
     uint32_t out_off;                    // K-C3: offset of the block inside its frame
 };
 #define ZKC_SEQSEC 16384u                // per-block scratch for the sequence section: [0,256) header, [256,..) bitstream
@@ -352,33 +353,68 @@ struct ZkcTabs { uint32_t ll_base[36], ml_base[53]; uint8_t ll_bits[36], ml_bits
 __device__ __forceinline__ uint32_t zkc_llc(const ZkcTabs& tb, uint32_t ll) { return ll < 64 ? tb.ll_code[ll] : (uint32_t)zk_highbit(ll) + 19; }
 __device__ __forceinline__ uint32_t zkc_mlc(const ZkcTabs& tb, uint32_t mlb) { return mlb < 128 ? tb.ml_code[mlb] : (uint32_t)zk_highbit(mlb) + 36; }
 
+// eight sequences in registers: the lanes of K-C2s stream through different blocks, so element-wise loads would stall the
+// warp on somebody's cache miss almost every iteration; 16-byte chunks are fetched one chunk ahead instead.
+struct ZkcSeq8 { uint4 ll, ml, o0, o1; };
+__device__ __forceinline__ void zkc_seq8_load(ZkcSeq8& r, const uint16_t* s_ll, const uint16_t* s_ml, const uint32_t* s_off, uint32_t chunk) {
+    r.ll = *(const uint4*)(s_ll + chunk * 8); r.ml = *(const uint4*)(s_ml + chunk * 8);
+    r.o0 = *(const uint4*)(s_off + chunk * 8); r.o1 = *(const uint4*)(s_off + chunk * 8 + 4);
+}
+__device__ __forceinline__ uint32_t zkc_u16_of(const uint4& v, int j) {
+    const uint32_t w = j < 2 ? v.x : (j < 4 ? v.y : (j < 6 ? v.z : v.w));
+    return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+__device__ __forceinline__ uint32_t zkc_u32_of(const uint4& a, const uint4& b, int j) {
+    return j == 0 ? a.x : (j == 1 ? a.y : (j == 2 ? a.z : (j == 3 ? a.w : (j == 4 ? b.x : (j == 5 ? b.y : (j == 6 ? b.z : b.w))))));
+}
+__device__ __forceinline__ void zkc_u32_set(uint4& a, uint4& b, int j, uint32_t v) {
+    if (j == 0) a.x = v; else if (j == 1) a.y = v; else if (j == 2) a.z = v; else if (j == 3) a.w = v;
+    else if (j == 4) b.x = v; else if (j == 5) b.y = v; else if (j == 6) b.z = v; else b.w = v;
+}
+
 // returns false if the section cannot be encoded within the scratch (the block then becomes a Raw block)
 __device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const uint16_t* s_ll, const uint16_t* s_ml, uint32_t* s_off, uint32_t nseq,
                                      bool first_block, uint8_t* out, uint32_t* hdr_bytes, uint32_t* bits_bytes) {
-    // repeat-offset substitution (serial history, A.5) turns s_off into Offset_Value in place.  Blocks are coded
-    // independently, so repeat codes are used only once three explicit offsets have been coded in this block (the
-    // decoder's history is then certain); the first block of a frame starts from the known {1,4,8}.
+    const uint32_t nchunks = (nseq + 7) / 8;
+    // ---- pass A (forward): repeat-offset substitution (serial history, A.5) turns s_off into Offset_Value in place, and the
+    // three code histograms are counted.  Blocks are coded independently, so repeat codes are used only once three explicit
+    // offsets have been coded in this block (the decoder's history is then certain); the first block of a frame starts from
+    // the known {1,4,8}.
+    for (int i = 0; i < 3 * 64; i++) (&sl.cnt[0][0])[i] = 0;
     {
         uint32_t r0 = 1, r1 = 4, r2 = 8, known = first_block ? 3 : 0;
-        for (uint32_t i = 0; i < nseq; i++) {
-            const uint32_t off = s_off[i], ll = s_ll[i];
-            uint32_t ov = off + 3;
-            if (known == 3) {
-                if (ll != 0) { if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3; }
-                else { if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3; }
+        ZkcSeq8 cur, nxt;
+        zkc_seq8_load(cur, s_ll, s_ml, s_off, 0);
+        for (uint32_t c = 0; c < nchunks; c++) {
+            if (c + 1 < nchunks) zkc_seq8_load(nxt, s_ll, s_ml, s_off, c + 1);
+            if ((c & 3) == 0 && c + 24 < nchunks) {     // pull the cache lines ~24 chunks ahead towards L1 (DRAM latency >> one chunk of work)
+                zk_prefetch_l1(s_off + (c + 24) * 8);
+                if ((c & 7) == 0) { zk_prefetch_l1(s_ll + (c + 24) * 8); zk_prefetch_l1(s_ml + (c + 24) * 8); }
             }
-            if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
-            else {
-                uint32_t idx = ov - 1 + (ll == 0);
-                if (idx == 1) { uint32_t t = r1; r1 = r0; r0 = t; }
-                else if (idx == 2) { uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
-                else if (idx == 3) { uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (c * 8 + j < nseq) {
+                    const uint32_t off = zkc_u32_of(cur.o0, cur.o1, j), ll = zkc_u16_of(cur.ll, j), mlb = zkc_u16_of(cur.ml, j);
+                    uint32_t ov = off + 3;
+                    if (known == 3) {
+                        if (ll != 0) { if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3; }
+                        else { if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3; }
+                    }
+                    if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
+                    else {
+                        uint32_t idx = ov - 1 + (ll == 0);
+                        if (idx == 1) { uint32_t t = r1; r1 = r0; r0 = t; }
+                        else if (idx == 2) { uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
+                        else if (idx == 3) { uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
+                    }
+                    zkc_u32_set(cur.o0, cur.o1, j, ov);
+                    sl.cnt[0][zkc_llc(tb, ll)]++; sl.cnt[1][zk_highbit(ov)]++; sl.cnt[2][zkc_mlc(tb, mlb)]++;
+                }
             }
-            s_off[i] = ov;
+            *(uint4*)(s_off + c * 8) = cur.o0; *(uint4*)(s_off + c * 8 + 4) = cur.o1;
+            cur = nxt;
         }
     }
-    for (int i = 0; i < 3 * 64; i++) (&sl.cnt[0][0])[i] = 0;
-    for (uint32_t i = 0; i < nseq; i++) { sl.cnt[0][zkc_llc(tb, s_ll[i])]++; sl.cnt[1][zk_highbit(s_off[i])]++; sl.cnt[2][zkc_mlc(tb, s_ml[i])]++; }
     uint32_t hp = 0;
     if (nseq < 128) out[hp++] = (uint8_t)nseq;
     else if (nseq < 0x7F00) { out[hp++] = (uint8_t)((nseq >> 8) + 128); out[hp++] = (uint8_t)nseq; }
@@ -404,25 +440,39 @@ __device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const ui
         }
     }
     out[modes_at] = (uint8_t)modes;
-    // backward bitstream: last sequence first (mirror of the decoder's order, A.5)
+    // ---- pass B (backward): the bitstream, last sequence first (mirror of the decoder's order, A.5)
     ZkcBitWW w; w.init(out + ZKC_SEQHDR, ZKC_SEQSEC - ZKC_SEQHDR);
-    uint32_t st_ll, st_of, st_ml;
-    uint32_t i = nseq - 1;
-    uint32_t llv = s_ll[i], mlb = s_ml[i], ov = s_off[i];
-    uint32_t llc = zkc_llc(tb, llv), mlc = zkc_mlc(tb, mlb), ofc = (uint32_t)zk_highbit(ov);
-    zkc_fse_init_state(sl.fse[2], mlc, st_ml); zkc_fse_init_state(sl.fse[1], ofc, st_of); zkc_fse_init_state(sl.fse[0], llc, st_ll);
-    w.add(llv - tb.ll_base[llc], tb.ll_bits[llc]);
-    w.add(mlb + 3 - tb.ml_base[mlc], tb.ml_bits[mlc]);
-    w.add(ov - (1u << ofc), (int)ofc);
-    while (i-- > 0) {
-        llv = s_ll[i]; mlb = s_ml[i]; ov = s_off[i];
-        llc = zkc_llc(tb, llv); mlc = zkc_mlc(tb, mlb); ofc = (uint32_t)zk_highbit(ov);
-        zkc_fse_encode(sl.fse[1], w, ofc, st_of);
-        zkc_fse_encode(sl.fse[2], w, mlc, st_ml);
-        zkc_fse_encode(sl.fse[0], w, llc, st_ll);
-        w.add(llv - tb.ll_base[llc], tb.ll_bits[llc]);
-        w.add(mlb + 3 - tb.ml_base[mlc], tb.ml_bits[mlc]);
-        w.add(ov - (1u << ofc), (int)ofc);
+    uint32_t st_ll = 0, st_of = 0, st_ml = 0;
+    bool first = true;
+    {
+        ZkcSeq8 cur, nxt;
+        zkc_seq8_load(cur, s_ll, s_ml, s_off, nchunks - 1);
+        for (uint32_t c = nchunks; c-- > 0;) {
+            if (c > 0) zkc_seq8_load(nxt, s_ll, s_ml, s_off, c - 1);
+            if ((c & 3) == 0 && c >= 24) {
+                zk_prefetch_l1(s_off + (c - 24) * 8);
+                if ((c & 7) == 0) { zk_prefetch_l1(s_ll + (c - 24) * 8); zk_prefetch_l1(s_ml + (c - 24) * 8); }
+            }
+#pragma unroll
+            for (int j = 7; j >= 0; j--) {
+                if (c * 8 + j < nseq) {
+                    const uint32_t llv = zkc_u16_of(cur.ll, j), mlb = zkc_u16_of(cur.ml, j), ov = zkc_u32_of(cur.o0, cur.o1, j);
+                    const uint32_t llc = zkc_llc(tb, llv), mlc = zkc_mlc(tb, mlb), ofc = (uint32_t)zk_highbit(ov);
+                    if (first) {
+                        zkc_fse_init_state(sl.fse[2], mlc, st_ml); zkc_fse_init_state(sl.fse[1], ofc, st_of); zkc_fse_init_state(sl.fse[0], llc, st_ll);
+                        first = false;
+                    } else {
+                        zkc_fse_encode(sl.fse[1], w, ofc, st_of);
+                        zkc_fse_encode(sl.fse[2], w, mlc, st_ml);
+                        zkc_fse_encode(sl.fse[0], w, llc, st_ll);
+                    }
+                    w.add(llv - tb.ll_base[llc], tb.ll_bits[llc]);
+                    w.add(mlb + 3 - tb.ml_base[mlc], tb.ml_bits[mlc]);
+                    w.add(ov - (1u << ofc), (int)ofc);
+                }
+            }
+            cur = nxt;
+        }
     }
     zkc_fse_flush(sl.fse[2], w, st_ml); zkc_fse_flush(sl.fse[1], w, st_of); zkc_fse_flush(sl.fse[0], w, st_ll);
     const uint32_t sb = w.finish();
@@ -532,7 +582,7 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
         size_t fend = fstart + a.frame_size < a.n ? fstart + a.frame_size : a.n;
         uint32_t nb_frame = (uint32_t)((fend - fstart + ZKC_BLOCK - 1) / ZKC_BLOCK); if (nb_frame == 0) nb_frame = 1;
         (void)f;
-        if (k_in_frame >= nb_frame) { if (lane == 0) a.blocks[b].csize = 0; return; }
+        if (k_in_frame >= nb_frame) { if (lane == 0) { a.blocks[b].csize = 0; a.blocks[b].lit_bytes = 0xFFFFFFFFu; } return; }
         // Last_Block flag
         sm.scratch[0] = (k_in_frame == nb_frame - 1) ? 1u : 0u;
     }
@@ -704,11 +754,27 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
         }
     }
 
-    // ------------------------------------------------------------------ sequences section (A.5): coded by K-C2s, moved into place here
+    // the sequences section is coded concurrently by K-C2s on another stream; zk_block_finish_kernel joins the two
+    if (lane == 0) { a.blocks[b].lit_bytes = raw_block ? 0u : opos; a.blocks[b].last_flag = last_flag; }
+}
+
+// K-C2f: join literals + sequences, fall back to a Raw block when that is not smaller, write the block header (A.2)
+__global__ void __launch_bounds__(128) zk_block_finish_kernel(ZkEncodeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= a.n_blocks) return;
+    const ZkcBlock bl = a.blocks[b];
+    if (bl.csize == 0 && bl.lit_bytes == 0xFFFFFFFFu) return;           // slot beyond the end of a short frame
+    size_t lo, hi, fstart;
+    zkc_block_range(a, b, lo, hi, fstart);
+    const uint32_t len = (uint32_t)(hi - lo);
+    uint8_t* out = a.stage + (size_t)b * ZKC_SLOT;
+    uint32_t opos = bl.lit_bytes;
+    bool raw_block = opos == 0;
     if (!raw_block) {
-        if (nseq == 0) { if (lane == 0) out[opos] = 0; opos += 1; }
+        if (bl.nseq == 0) { if (lane == 0) out[opos] = 0; opos += 1; }
         else {
-            const uint32_t hp = a.blocks[b].seq_hdr, sb = a.blocks[b].seq_bits;
+            const uint32_t hp = bl.seq_hdr, sb = bl.seq_bits;
             if (!hp || opos + hp + sb >= len + 3) raw_block = true;
             else {
                 const uint8_t* sec = a.seqsec + (size_t)b * ZKC_SEQSEC;
@@ -720,15 +786,12 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
         }
     }
     if (!raw_block && opos >= len + 3) raw_block = true;
-
-    // ------------------------------------------------------------------ block header (A.2)
     if (raw_block) {
-        __syncwarp();          // lane 0 may already have written section headers into the slot: order them before the copy
         for (uint32_t i = lane; i < len; i += 32) out[3 + i] = a.src[lo + i];
         opos = 3 + len;
     }
     if (lane == 0) {
-        uint32_t bh = last_flag | ((raw_block ? 0u : 2u) << 1) | ((raw_block ? len : opos - 3) << 3);
+        uint32_t bh = bl.last_flag | ((raw_block ? 0u : 2u) << 1) | ((raw_block ? len : opos - 3) << 3);
         out[0] = (uint8_t)bh; out[1] = (uint8_t)(bh >> 8); out[2] = (uint8_t)(bh >> 16);
         a.blocks[b].csize = opos;
     }
@@ -882,6 +945,9 @@ size_t zk_encode_bound(size_t n, uint32_t frame_size) {
 void zk_encode_ws_free(ZkEncodeWs* ws) {
     if (ws->buf) cudaFree(ws->buf);
     if (ws->h_sizes) cudaFreeHost(ws->h_sizes);
+    if (ws->side) cudaStreamDestroy(ws->side);
+    if (ws->ev_a) cudaEventDestroy(ws->ev_a);
+    if (ws->ev_b) cudaEventDestroy(ws->ev_b);
     ws->prof.destroy();
     *ws = ZkEncodeWs();
 }
@@ -939,9 +1005,20 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ws->prof.end(5, stream);
     const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqSlot) * ZKC_SEQ_LANES;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
+    // the two entropy kernels are independent and both latency-bound: run them side by side, join in zk_block_finish_kernel
+    if (!ws->side) {
+        ZKC_CUDA_OK(cudaStreamCreateWithFlags(&ws->side, cudaStreamNonBlocking));
+        ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming));
+        ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming));
+    }
     ws->prof.begin(6, stream);
-    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SEQ_LANES - 1) / ZKC_SEQ_LANES), 32, seq_smem, stream, a);
+    ZKC_CUDA_OK(cudaEventRecord(ws->ev_a, stream));
+    ZKC_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_a, 0));
+    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SEQ_LANES - 1) / ZKC_SEQ_LANES), 32, seq_smem, ws->side, a);
+    ZKC_CUDA_OK(cudaEventRecord(ws->ev_b, ws->side));
     ZK_LAUNCH(zk_lit_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
+    ZKC_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_b, 0));
+    ZK_LAUNCH(zk_block_finish_kernel, (uint32_t)((n_blocks + 3) / 4), 128, 0, stream, a);
     ws->prof.end(6, stream);
     ws->prof.begin(7, stream);
     if (checksum) ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, stream, a);
@@ -951,7 +1028,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ws->prof.end(7, stream);
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes, a.frame_csize, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, stream));
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes + ws->cap_frames, a.total, 16, cudaMemcpyDeviceToHost, stream));
-    ws->launches += 6 + (checksum ? 1 : 0);
+    ws->launches += 7 + (checksum ? 1 : 0);
     ws->pending_frames = n_frames;
     return 0;
 }
