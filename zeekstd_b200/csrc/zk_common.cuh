@@ -15,7 +15,7 @@
 #include <cuda_runtime.h>
 #define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ZK_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
-#define ZK_SPIN() __nanosleep(64)
+#define ZK_SPIN() __nanosleep(32)
 #endif
 
 #include <stdint.h>

@@ -606,8 +606,10 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
 #define ZK_LONG 48u     // literal runs / matches at least this long are copied by the whole warp
 
 struct ZkD2Smem {
-    volatile uint32_t done_pos;      // every output byte below this position (entry-relative) is final and in HBM
-    volatile uint32_t done_chunk;    // chunks [0, done_chunk) are published
+    volatile uint32_t done_pos;      // every output byte below this position (entry-relative) is final (in the ring)
+    volatile uint32_t done_chunk;    // chunks [0, done_chunk) are done
+    volatile uint32_t flushed_pos;   // ... and below this position it is in HBM too (the flush is off the critical chain)
+    volatile uint32_t flushed_chunk;
     volatile int abort_code;
 };
 
@@ -700,7 +702,7 @@ __device__ __forceinline__ void zk_ring_reload(const ZkRing& rg, uint32_t s, uin
     }
 }
 
-// wait until it is chunk c's turn, then publish its end position
+// wait until it is chunk c's turn, then publish that its bytes are final (readable from the ring)
 __device__ __forceinline__ void zk_d2_publish(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, int lane) {
     __threadfence_block();
     __syncwarp();
@@ -712,16 +714,29 @@ __device__ __forceinline__ void zk_d2_publish(ZkD2Smem& sm, uint32_t c, uint32_t
     }
     __syncwarp();
 }
+// ... and, after the flush, that they are in HBM (far readers and ring reuse depend on this one)
+__device__ __forceinline__ void zk_d2_publish_flushed(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        while (sm.flushed_chunk != c && sm.abort_code == 0) ZK_SPIN();
+        sm.flushed_pos = end_pos;
+        __threadfence_block();
+        sm.flushed_chunk = c + 1;
+    }
+    __syncwarp();
+}
 
 // warp-uniform wait: returns false if the CTA aborted.  Waits until chunk c may start:
-// exclusive == false: its end lies within `window` of done_pos;  exclusive == true: it is the oldest chunk.
+// exclusive == false: its end lies within `window` of flushed_pos (the in-flight region never laps the ring);
+// exclusive == true: every earlier chunk is done and flushed (the chunk then runs alone, HBM to HBM).
 __device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, uint32_t window, bool exclusive, int lane) {
     for (;;) {
         uint32_t ok = 0, ab = 0;
         if (lane == 0) {
             ab = sm.abort_code != 0;
-            uint32_t dc = sm.done_chunk, dp = sm.done_pos;
-            ok = exclusive ? (dc == c) : (dc == c || end_pos - dp <= window);
+            uint32_t fc = sm.flushed_chunk, fp = sm.flushed_pos;
+            ok = exclusive ? (fc == c) : (fc == c || end_pos - fp <= window);
             __threadfence_block();
         }
         ok = __shfl_sync(0xFFFFFFFFu, ok, 0); ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
@@ -739,7 +754,7 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     ZkEntry ent = a.entries[e];
     if (ent.status != 0 || a.counters->overflow) return;
-    if (threadIdx.x == 0) { sm.done_pos = 0; sm.done_chunk = 0; sm.abort_code = 0; }
+    if (threadIdx.x == 0) { sm.done_pos = 0; sm.done_chunk = 0; sm.flushed_pos = 0; sm.flushed_chunk = 0; sm.abort_code = 0; }
     __syncthreads();
     uint8_t* out = a.dst + a.d_off[e];
     const unsigned long long cap64 = a.d_off[e + 1] - a.d_off[e];
@@ -773,6 +788,7 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                 __syncwarp();
                 { uint32_t en = pos + blk.regen; zk_ring_reload(rg, en > half ? en - half : 0, en, lane, 32); }
                 zk_d2_publish(sm, c, pos + blk.regen, lane);
+                zk_d2_publish_flushed(sm, c, pos + blk.regen, lane);
                 continue;
             }
             const uint32_t* s_lit = a.seq_lit_end + blk.seq_base;
@@ -789,12 +805,13 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                     else zk_warp_copy(out + st0, lit + le, n, lane);
                     __syncwarp();
                     zk_ring_reload(rg, en - half, en, lane, 32);
+                    zk_d2_publish(sm, c, en, lane);
                 } else {
                     for (uint32_t i = lane; i < n; i += 32) rg.at(st0 + i) = blk.lit_kind == 1 ? blk.lit_byte : lit[le + i];
-                    __syncwarp();
+                    zk_d2_publish(sm, c, en, lane);
                     zk_ring_flush(rg, st0, en, lane);
                 }
-                zk_d2_publish(sm, c, en, lane);
+                zk_d2_publish_flushed(sm, c, en, lane);
                 continue;
             }
             // ---------------- 32 sequences, one per lane
@@ -860,6 +877,7 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                 }
                 zk_ring_reload(rg, chunk_end - half, chunk_end, lane, 32);
                 zk_d2_publish(sm, c, chunk_end, lane);
+                zk_d2_publish_flushed(sm, c, chunk_end, lane);
                 continue;
             }
 
@@ -886,17 +904,19 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
             bool aborted = false;
             while (pending) {
                 // lane 0 samples the pipeline state; everything below is warp-uniform
-                uint32_t dc = 0, dp = 0, ab = 0;
-                if (lane == 0) { dc = sm.done_chunk; dp = sm.done_pos; ab = sm.abort_code != 0; __threadfence_block(); }
-                dc = __shfl_sync(0xFFFFFFFFu, dc, 0); dp = __shfl_sync(0xFFFFFFFFu, dp, 0); ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
+                uint32_t dc = 0, dp = 0, fp = 0, ab = 0;
+                if (lane == 0) { dc = sm.done_chunk; dp = sm.done_pos; fp = sm.flushed_pos; ab = sm.abort_code != 0; __threadfence_block(); }
+                dc = __shfl_sync(0xFFFFFFFFu, dc, 0); dp = __shfl_sync(0xFFFFFFFFu, dp, 0); fp = __shfl_sync(0xFFFFFFFFu, fp, 0);
+                ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
                 __syncwarp();                      // orders the other lanes' data reads after lane 0's acquire
                 if (ab) { aborted = true; break; }
                 const bool oldest = dc == c;
                 const int first = __ffs((int)pending) - 1;
                 const uint32_t md_first = __shfl_sync(0xFFFFFFFFu, md, first);
-                const uint32_t frontier = oldest ? md_first : dp;
+                const uint32_t frontier = oldest ? md_first : dp;        // bytes below it are final in the ring
                 const bool mine = (pending >> lane) & 1;
-                const bool ready = mine && (need_end <= frontier || (oldest && lane == first));
+                // near sources come from the ring (final is enough); far sources from HBM (must be flushed)
+                const bool ready = mine && (near_src ? (need_end <= frontier || (oldest && lane == first)) : need_end <= fp);
                 const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, ready);
                 if (!rmask) { ZK_SPIN(); continue; }
                 if (ready && ml < ZK_LONG) {
@@ -920,8 +940,9 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                 pending &= ~rmask;
             }
             if (aborted) break;
-            zk_ring_flush(rg, chunk_start, chunk_end, lane);
-            zk_d2_publish(sm, c, chunk_end, lane);
+            zk_d2_publish(sm, c, chunk_end, lane);                 // dependants can read the ring now ...
+            zk_ring_flush(rg, chunk_start, chunk_end, lane);       // ... while the HBM flush happens off the critical chain
+            zk_d2_publish_flushed(sm, c, chunk_end, lane);
         }
         // advance to the next block
         if (has_seq) {
