@@ -158,3 +158,16 @@ def test_random_offset_reads(ctx):
         dec.set_offset(o); dec.set_offset_limit(o + 65536)
         assert dec.read_all() == x[o:o + 65536].tobytes()
         dec.set_offset_limit(x.size)
+
+
+def test_batched_range_reads(ctx):
+    """seek.read_ranges == per-request Decoder semantics, including reads that straddle frames and batch boundaries"""
+    from zeekstd_b200 import seek
+    x = corpus.make_mix(24 << 20, seed=11, device="cuda").cpu().numpy()
+    a, st = O.ref_seekable_archive(x, 1 << 20, 1, False, threads=os.cpu_count())
+    arch = np.frombuffer(a + b"\0" * 64, dtype=np.uint8)
+    rng = np.random.default_rng(1)
+    offs = np.concatenate([rng.integers(0, x.size - 70_000, 200), np.arange(1, 20) * (1 << 20) - 1000])   # some cross frame borders
+    outs, nfr = seek.read_ranges(ctx, arch, np.array(st.c), np.array(st.d), offs, 70_000, max_batch_bytes=3 << 20)
+    for o, got in zip(offs, outs):
+        assert got == x[int(o): int(o) + 70_000].tobytes()

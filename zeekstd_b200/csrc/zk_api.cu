@@ -90,6 +90,7 @@ extern "C" int32_t zk_ctx_create(int32_t device_ordinal, uint32_t flags, zk_ctx*
         if (cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZK_ERR_NO_DEVICE; }
         c->slot[i].dws.sm_count = c->sm_count;
         c->slot[i].dws.ring_override = (uint32_t)zk_env_size("ZK_RING_BYTES", 0);   // tuning / tests: power of two >= 1024
+        c->slot[i].dws.huf_pad = (uint32_t)zk_env_size("ZK_HUF_PAD", 0);
         c->slot[i].ews.sm_count = c->sm_count;
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);

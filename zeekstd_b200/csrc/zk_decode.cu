@@ -1151,7 +1151,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     const size_t seq_smem = sizeof(ZkSeqSlot) * ZK_SEQ_LANES, huf_smem = sizeof(ZkHufSlot) * ZK_HUF_SLOTS;
     if (!ws->attr_set) {
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
-        ZK_CUDA_OK(cudaFuncSetAttribute(zk_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem));
+        ZK_CUDA_OK(cudaFuncSetAttribute(zk_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem + 65536));
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         ws->attr_set = true;
     }
@@ -1168,7 +1168,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     ZK_CUDA_OK(cudaEventRecord(ws->ev_scan, stream));
     ZK_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_scan, 0));
     ws->prof.begin(2, ws->side);
-    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem, ws->side, a);
+    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem + ws->huf_pad, ws->side, a);
     ws->prof.end(2, ws->side);
     ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, ws->side));
     ws->prof.begin(1, stream);

@@ -24,6 +24,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint64_t* c_off = nullptr; uint64_t* d_off = nullptr;
     uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
     bool attr_set = false; uint32_t ring_override = 0;
+    uint32_t huf_pad = 0;             // extra dynamic smem per Huffman CTA: fewer resident CTAs -> more L1 for the streams (tuning)
     int share = 1;                    // how many batches share the GPU concurrently (host pipeline depth)
     cudaStream_t side = nullptr; cudaEvent_t ev_scan = nullptr, ev_huf = nullptr;   // Huffman kernel runs beside the FSE kernel
     ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
