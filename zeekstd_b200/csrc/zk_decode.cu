@@ -15,6 +15,8 @@
 // reference tree).  All integer/byte work; no tensor cores.
 #include "zk_common.cuh"
 #include "zk_decode.h"
+#include <stdio.h>
+#include <stdlib.h>
 
 // =============================================================================================
 // K-D0: header scan
@@ -605,17 +607,51 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
 // =============================================================================================
 #define ZK_LONG 48u     // literal runs / matches at least this long are copied by the whole warp
 
-struct ZkD2Smem {
-    volatile uint32_t done_pos;      // every output byte below this position (entry-relative) is final (in the ring)
-    volatile uint32_t done_chunk;    // chunks [0, done_chunk) are done
-    volatile uint32_t flushed_pos;   // ... and below this position it is in HBM too (the flush is off the critical chain)
-    volatile uint32_t flushed_chunk;
-    volatile int abort_code;
-};
+#define ZK_D2_META 64u          // chunk descriptors kept in shared memory (chunks between the oldest unflushed and the newest started)
 
-__device__ __forceinline__ void zk_d2_abort(ZkD2Smem& sm, int code) { atomicCAS((int*)&sm.abort_code, 0, code); }
+struct ZkD2Smem {
+    // in-order prefixes, advanced co-operatively by whoever polls ("helping"); nobody ever waits for a predecessor to publish
+    uint32_t done_pos, done_chunk;         // every byte below done_pos is final (readable from the ring); chunks [0, done_chunk) are done
+    uint32_t flushed_pos, flushed_chunk;   // ... and below flushed_pos it is in HBM too
+    int abort_code;
+    // per-chunk descriptors, slot = chunk & (ZK_D2_META-1); a field is valid for chunk k iff its tag == k + 1
+    uint32_t started[ZK_D2_META], start[ZK_D2_META], end[ZK_D2_META], done[ZK_D2_META], flushed[ZK_D2_META];
+    // per-SEQUENCE completion inside a chunk (the dependency chain of a frame runs sequence to sequence, not chunk to chunk):
+    uint32_t oe[ZK_D2_META][32];          // end position of each of the chunk's 32 sequences (non-decreasing; lanes past the last = chunk end)
+    uint32_t dmask[ZK_D2_META];           // bit j: sequence j is completely written (literals + match)
+    uint32_t litdone[ZK_D2_META];         // tag: every literal run of the chunk is in place
+};
+#define ZK_VOL(x) (*(volatile uint32_t*)&(x))
+
+__device__ __forceinline__ void zk_d2_abort(ZkD2Smem& sm, int code) { atomicCAS(&sm.abort_code, 0, code); }
 // warp-uniform view of the abort flag (every lane must take the same branch around collectives)
-__device__ __forceinline__ bool zk_d2_aborted(ZkD2Smem& sm) { return __any_sync(0xFFFFFFFFu, sm.abort_code != 0); }
+__device__ __forceinline__ bool zk_d2_aborted(ZkD2Smem& sm) { return __any_sync(0xFFFFFFFFu, *(volatile int*)&sm.abort_code != 0); }
+
+// advance the in-order prefixes as far as the per-chunk flags allow (any thread may do this at any time)
+__device__ __forceinline__ void zk_d2_help(ZkD2Smem& sm) {
+    uint32_t dc = ZK_VOL(sm.done_chunk), dc0 = dc, dp = 0;
+    while (ZK_VOL(sm.done[dc & (ZK_D2_META - 1)]) == dc + 1) { dp = ZK_VOL(sm.end[dc & (ZK_D2_META - 1)]); dc++; }
+    if (dc != dc0) { atomicMax(&sm.done_pos, dp); __threadfence_block(); atomicMax(&sm.done_chunk, dc); }
+    uint32_t fc = ZK_VOL(sm.flushed_chunk), fc0 = fc, fp = 0;
+    while (ZK_VOL(sm.flushed[fc & (ZK_D2_META - 1)]) == fc + 1) { fp = ZK_VOL(sm.end[fc & (ZK_D2_META - 1)]); fc++; }
+    if (fc != fc0) { atomicMax(&sm.flushed_pos, fp); __threadfence_block(); atomicMax(&sm.flushed_chunk, fc); }
+}
+
+// Are all bytes of [src0, need_end) that lie BEFORE this chunk final?  (lane-level; scans the descriptors of the chunks in flight)
+__device__ __forceinline__ bool zk_d2_ext_ready(ZkD2Smem& sm, uint32_t c, uint32_t src0, uint32_t need_end, uint32_t chunk_start) {
+    if (src0 >= chunk_start) return true;                               // purely intra-chunk
+    const uint32_t ne = need_end < chunk_start ? need_end : chunk_start;
+    if (ne <= ZK_VOL(sm.done_pos)) return true;
+    const uint32_t dc = ZK_VOL(sm.done_chunk);
+    for (uint32_t k = c; k-- > dc;) {
+        const uint32_t e = k & (ZK_D2_META - 1);
+        if (ZK_VOL(sm.started[e]) != k + 1) return false;               // its range is not known yet
+        const uint32_t sk = ZK_VOL(sm.start[e]), ek = ZK_VOL(sm.end[e]);
+        if (sk < ne && ek > src0 && ZK_VOL(sm.done[e]) != k + 1) return false;
+        if (sk <= src0) return true;                                    // older chunks end at or before src0
+    }
+    return true;                                                         // reached the done prefix
+}
 
 // warp-cooperative copy of n bytes HBM -> HBM, non-overlapping (or src entirely before dst with distance >= n)
 __device__ __forceinline__ void zk_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
@@ -676,6 +712,26 @@ __device__ __forceinline__ void zk_warp_match(uint8_t* dst, uint32_t off, uint32
 struct ZkRing {
     uint8_t* ring; uint32_t mask, mis; uint8_t* out;
     __device__ __forceinline__ uint8_t& at(uint32_t p) const { return ring[(p + mis) & mask]; }
+    // unaligned 8-byte read of positions [p, p+8) (three aligned word reads, wrap-safe)
+    __device__ __forceinline__ unsigned long long ld8(uint32_t p) const {
+        const uint32_t idx = (p + mis) & mask, wi = idx & ~3u, sh = (idx & 3u) * 8u;
+        const uint32_t w0 = *(const uint32_t*)(ring + wi), w1 = *(const uint32_t*)(ring + ((wi + 4) & mask)), w2 = *(const uint32_t*)(ring + ((wi + 8) & mask));
+        return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+    }
+    // lane-local match copy inside the ring: 16 bytes per step when the period allows it (a byte loop costs one dependent
+    // shared-memory round trip per byte, and this copy sits on the critical dependency chain of the frame)
+    __device__ __forceinline__ void copy_near(uint32_t dst, uint32_t src, uint32_t n) const {
+        if (dst - src >= 16) {
+            for (uint32_t i = 0; i < n; i += 16) {
+                unsigned long long v0 = ld8(src + i), v1 = ld8(src + i + 8);
+                const uint32_t k = n - i < 16 ? n - i : 16;
+                for (uint32_t q = 0; q < k; q++) {
+                    at(dst + i + q) = (uint8_t)(q < 8 ? v0 : v1);
+                    if (q < 8) v0 >>= 8; else v1 >>= 8;
+                }
+            }
+        } else for (uint32_t i = 0; i < n; i++) at(dst + i) = at(src + i);
+    }
 };
 
 // flush [s, e) ring -> HBM: full 16-byte groups with vector stores, ragged ends bytewise (neighbours own the rest)
@@ -702,41 +758,101 @@ __device__ __forceinline__ void zk_ring_reload(const ZkRing& rg, uint32_t s, uin
     }
 }
 
-// wait until it is chunk c's turn, then publish that its bytes are final (readable from the ring)
-__device__ __forceinline__ void zk_d2_publish(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, int lane) {
+// unaligned 8-byte little-endian load from HBM (three aligned 4-byte loads issued back to back)
+__device__ __forceinline__ unsigned long long zk_ld8_unaligned(const uint8_t* p) {
+    uintptr_t a = (uintptr_t)p; uint32_t mis = (uint32_t)(a & 3);
+    const uint32_t* q = (const uint32_t*)(a - mis);
+    uint32_t w0 = q[0], w1 = q[1];
+    if (mis == 0) return (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+    uint32_t w2 = q[2], sh = mis * 8;
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// Place the literal runs of one chunk.  The runs are CONTIGUOUS in the block's literal buffer ([lit_lo, lit_hi)), so the
+// warp reads them with coalesced loads, 32 bytes a step, and every byte finds its destination by a 5-step search over the
+// lanes' cumulative literal ends (le is non-decreasing across lanes).  A per-lane byte loop paid one HBM round trip per
+// byte and was the real bottleneck of the first exec kernels.  TO_RING: destination is the ring, else HBM directly.
+template <bool TO_RING>
+__device__ __forceinline__ void zk_chunk_literals(const ZkRing& rg, const uint8_t* lit, int lit_kind, uint32_t lit_byte, uint32_t le, uint32_t le_prev,
+                                                  uint32_t o_lit, int lane) {
+    const uint32_t lit_lo = __shfl_sync(0xFFFFFFFFu, le_prev, 0), lit_hi = __shfl_sync(0xFFFFFFFFu, le, 31);
+    for (uint32_t base = lit_lo; base < lit_hi; base += 256) {
+        // issue up to eight coalesced 32-byte loads first (one memory latency for 256 literal bytes), then place them
+        uint32_t bytes[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t t = base + u * 32 + lane;
+            bytes[u] = lit_byte;
+            if (t < lit_hi && lit_kind != 1) bytes[u] = lit[t];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t t = base + u * 32 + lane;
+            if (base + u * 32 >= lit_hi) break;           // warp-uniform
+            const bool active = t < lit_hi;
+            int lo = 0, hi = 31;                          // owner = first lane whose le > t
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, le, mid);
+                if (v > t) hi = mid; else lo = mid + 1;
+            }
+            const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, o_lit, lo), l0 = __shfl_sync(0xFFFFFFFFu, le_prev, lo);
+            if (active) {
+                const uint32_t dest = d0 + (t - l0);
+                if (TO_RING) rg.at(dest) = (uint8_t)bytes[u]; else rg.out[dest] = (uint8_t)bytes[u];
+            }
+        }
+    }
+}
+
+// chunk c's bytes are final in the ring: dependants may read them
+__device__ __forceinline__ void zk_d2_mark_done(ZkD2Smem& sm, uint32_t c, int lane) {
     __threadfence_block();
     __syncwarp();
     if (lane == 0) {
-        while (sm.done_chunk != c && sm.abort_code == 0) ZK_SPIN();
-        sm.done_pos = end_pos;
-        __threadfence_block();
-        sm.done_chunk = c + 1;
+        const uint32_t e = c & (ZK_D2_META - 1);
+        ZK_VOL(sm.dmask[e]) = 0xFFFFFFFFu; ZK_VOL(sm.litdone[e]) = c + 1; ZK_VOL(sm.done[e]) = c + 1;
+        zk_d2_help(sm);
     }
     __syncwarp();
 }
-// ... and, after the flush, that they are in HBM (far readers and ring reuse depend on this one)
-__device__ __forceinline__ void zk_d2_publish_flushed(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, int lane) {
+// ... and now they are in HBM as well (far readers and ring reuse depend on this one)
+__device__ __forceinline__ void zk_d2_mark_flushed(ZkD2Smem& sm, uint32_t c, int lane) {
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) {
-        while (sm.flushed_chunk != c && sm.abort_code == 0) ZK_SPIN();
-        sm.flushed_pos = end_pos;
-        __threadfence_block();
-        sm.flushed_chunk = c + 1;
-    }
+    if (lane == 0) { ZK_VOL(sm.flushed[c & (ZK_D2_META - 1)]) = c + 1; zk_d2_help(sm); }
     __syncwarp();
 }
 
-// warp-uniform wait: returns false if the CTA aborted.  Waits until chunk c may start:
+// announce chunk c = [start_pos, end_pos) and the end position of each of its sequences (seq_end per lane)
+__device__ __forceinline__ void zk_d2_announce(ZkD2Smem& sm, uint32_t c, uint32_t start_pos, uint32_t end_pos, uint32_t seq_end, uint32_t premask, int lane) {
+    const uint32_t e = c & (ZK_D2_META - 1);
+    ZK_VOL(sm.oe[e][lane]) = seq_end;
+    if (lane == 0) { ZK_VOL(sm.start[e]) = start_pos; ZK_VOL(sm.end[e]) = end_pos; ZK_VOL(sm.dmask[e]) = premask; }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) ZK_VOL(sm.started[e]) = c + 1;
+    __syncwarp();
+}
+// sequences `mask` of chunk c are completely written
+__device__ __forceinline__ void zk_d2_progress(ZkD2Smem& sm, uint32_t c, uint32_t mask, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0 && mask) atomicOr(&sm.dmask[c & (ZK_D2_META - 1)], mask);
+}
+
+// warp-uniform wait until chunk c = [start_pos, end_pos) may start.  Returns false if the CTA aborted.
 // exclusive == false: its end lies within `window` of flushed_pos (the in-flight region never laps the ring);
 // exclusive == true: every earlier chunk is done and flushed (the chunk then runs alone, HBM to HBM).
-__device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint32_t end_pos, uint32_t window, bool exclusive, int lane) {
+__device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint32_t start_pos, uint32_t end_pos, uint32_t window, bool exclusive, int lane) {
     for (;;) {
         uint32_t ok = 0, ab = 0;
         if (lane == 0) {
-            ab = sm.abort_code != 0;
-            uint32_t fc = sm.flushed_chunk, fp = sm.flushed_pos;
-            ok = exclusive ? (fc == c) : (fc == c || end_pos - fp <= window);
+            zk_d2_help(sm);
+            ab = *(volatile int*)&sm.abort_code != 0;
+            const uint32_t fc = ZK_VOL(sm.flushed_chunk), fp = ZK_VOL(sm.flushed_pos);
+            ok = exclusive ? (fc == c) : (fc == c || (end_pos - fp <= window && c - fc < ZK_D2_META - 2));
             __threadfence_block();
         }
         ok = __shfl_sync(0xFFFFFFFFu, ok, 0); ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
@@ -755,6 +871,7 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
     ZkEntry ent = a.entries[e];
     if (ent.status != 0 || a.counters->overflow) return;
     if (threadIdx.x == 0) { sm.done_pos = 0; sm.done_chunk = 0; sm.flushed_pos = 0; sm.flushed_chunk = 0; sm.abort_code = 0; }
+    for (uint32_t i = threadIdx.x; i < ZK_D2_META; i += blockDim.x) { sm.started[i] = 0; sm.done[i] = 0; sm.flushed[i] = 0; sm.litdone[i] = 0; }
     __syncthreads();
     uint8_t* out = a.dst + a.d_off[e];
     const unsigned long long cap64 = a.d_off[e + 1] - a.d_off[e];
@@ -765,6 +882,7 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
 
     uint32_t pos = 0, zstart = 0, chunk_base = 0;
     uint32_t R0 = 1, R1 = 4, R2 = 8;
+    uint32_t preannounced = 0xFFFFFFFFu;          // chunk id this warp has already announced ahead of time
     for (uint32_t bi = 0; bi < ent.n_blocks; bi++) {
         if (zk_d2_aborted(sm)) break;
         const uint32_t bidx = ent.first_block + bi;
@@ -780,15 +898,16 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
             const uint32_t j = c - chunk_base;
             if (!has_seq) {
                 // ---------------- Raw block / RLE block / literals-only compressed block: direct path, runs alone
-                if (!zk_d2_wait_start(sm, c, 0, 0, true, lane)) break;
+                if (!zk_d2_wait_start(sm, c, pos, pos + blk.regen, 0, true, lane)) break;
+                zk_d2_announce(sm, c, pos, pos + blk.regen, pos + blk.regen, 0u, lane);
                 if (blk.type == 0) zk_warp_copy(out + pos, ebase + blk.src, blk.size, lane);
                 else if (blk.type == 1) zk_warp_fill(out + pos, ebase[blk.src], blk.size, lane);
                 else if (blk.lit_kind == 1) zk_warp_fill(out + pos, blk.lit_byte, blk.lit_size, lane);
                 else zk_warp_copy(out + pos, blk.lit_kind == 0 ? ebase + blk.lit_src : a.lit + blk.lit_base, blk.lit_size, lane);
                 __syncwarp();
                 { uint32_t en = pos + blk.regen; zk_ring_reload(rg, en > half ? en - half : 0, en, lane, 32); }
-                zk_d2_publish(sm, c, pos + blk.regen, lane);
-                zk_d2_publish_flushed(sm, c, pos + blk.regen, lane);
+                zk_d2_mark_done(sm, c, lane);
+                zk_d2_mark_flushed(sm, c, lane);
                 continue;
             }
             const uint32_t* s_lit = a.seq_lit_end + blk.seq_base;
@@ -799,26 +918,37 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                 const uint32_t le = s_lit[blk.nseq - 1], oe = s_out[blk.nseq - 1];
                 const uint32_t n = blk.lit_size - le, st0 = pos + oe, en = pos + blk.regen;
                 const bool direct = n > half;
-                if (!zk_d2_wait_start(sm, c, en, half, direct, lane)) break;
+                if (!zk_d2_wait_start(sm, c, st0, en, half, direct, lane)) break;
+                zk_d2_announce(sm, c, st0, en, en, 0u, lane);
                 if (direct) {
                     if (blk.lit_kind == 1) zk_warp_fill(out + st0, blk.lit_byte, n, lane);
                     else zk_warp_copy(out + st0, lit + le, n, lane);
                     __syncwarp();
                     zk_ring_reload(rg, en - half, en, lane, 32);
-                    zk_d2_publish(sm, c, en, lane);
+                    zk_d2_mark_done(sm, c, lane);
                 } else {
                     for (uint32_t i = lane; i < n; i += 32) rg.at(st0 + i) = blk.lit_kind == 1 ? blk.lit_byte : lit[le + i];
-                    zk_d2_publish(sm, c, en, lane);
+                    zk_d2_mark_done(sm, c, lane);
                     zk_ring_flush(rg, st0, en, lane);
                 }
-                zk_d2_publish_flushed(sm, c, en, lane);
+                zk_d2_mark_flushed(sm, c, lane);
                 continue;
             }
             // ---------------- 32 sequences, one per lane
+#ifndef ZK_EMUL
+#define ZK_STAMP(k) do { if (a.trace && e == 0 && c < 1024 && lane == 0) a.trace[c * 8 + (k)] = clock64(); } while (0)
+#else
+#define ZK_STAMP(k) do { } while (0)
+#endif
+            ZK_STAMP(0);
             const uint32_t s = j * 32 + lane;
             const bool valid = s < blk.nseq;
             uint32_t le = 0, oe = 0, offv = 0;
-            if (valid) { le = s_lit[s]; oe = s_out[s]; offv = a.seq_off[blk.seq_base + s]; }
+            {   // lanes past the last sequence of the block repeat its cumulative ends (zero-length runs; keeps `le` monotone)
+                const uint32_t sc = valid ? s : blk.nseq - 1;
+                le = s_lit[sc]; oe = s_out[sc];
+                if (valid) offv = a.seq_off[blk.seq_base + s];
+            }
             uint32_t le_prev = __shfl_up_sync(0xFFFFFFFFu, le, 1), oe_prev = __shfl_up_sync(0xFFFFFFFFu, oe, 1);
             if (lane == 0) { le_prev = s ? s_lit[s - 1] : 0; oe_prev = s ? s_out[s - 1] : 0; }
             const uint32_t ll = le - le_prev, ml = (oe - oe_prev) - ll;
@@ -837,21 +967,49 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
             const uint32_t chunk_start = pos + __shfl_sync(0xFFFFFFFFu, oe_prev, 0);
             const uint32_t chunk_end = pos + __shfl_sync(0xFFFFFFFFu, oe, min(31u, blk.nseq - 1 - j * 32));
             const bool direct = chunk_end - chunk_start > half;
-            if (!zk_d2_wait_start(sm, c, chunk_end, half, direct, lane)) break;
+            ZK_STAMP(1);
+            if (!zk_d2_wait_start(sm, c, chunk_start, chunk_end, half, direct, lane)) break;
+            if (preannounced != c) zk_d2_announce(sm, c, chunk_start, chunk_end, pos + oe, 0u, lane);
+            // Announce this warp's NEXT chunk of the block right away (its sequence ends are one coalesced load away): chunks of
+            // other warps that depend on it can then resolve their producers without waiting for this warp to get there.
+            {
+                const uint32_t jn = j + (uint32_t)W;
+                if (jn < nchunks - 1) {
+                    uint32_t okp = 0;
+                    if (lane == 0) okp = (c + (uint32_t)W) - ZK_VOL(sm.flushed_chunk) < ZK_D2_META - 2;
+                    if (__shfl_sync(0xFFFFFFFFu, okp, 0)) {
+                        const uint32_t sn = jn * 32 + lane, scn = sn < blk.nseq ? sn : blk.nseq - 1;
+                        const uint32_t oen = s_out[scn];
+                        uint32_t stn = 0;
+                        if (lane == 0) stn = s_out[jn * 32 - 1];
+                        stn = __shfl_sync(0xFFFFFFFFu, stn, 0);
+                        const uint32_t enn = __shfl_sync(0xFFFFFFFFu, oen, 31);
+                        zk_d2_announce(sm, c + (uint32_t)W, pos + stn, pos + enn, pos + oen, 0u, lane);
+                        preannounced = c + (uint32_t)W;
+                    }
+                }
+            }
+            ZK_STAMP(2);
 
             if (direct) {
                 // ======== huge chunk: HBM -> HBM, alone in flight (it is the oldest chunk)
-                if (valid && ll < ZK_LONG) {
-                    uint8_t* d = out + o_lit;
-                    if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) d[i] = blk.lit_byte;
-                    else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) d[i] = sp[i]; }
-                }
-                uint32_t longlit = __ballot_sync(0xFFFFFFFFu, valid && ll >= ZK_LONG);
-                while (longlit) {
-                    int l = __ffs((int)longlit) - 1; longlit &= longlit - 1;
-                    uint32_t n = __shfl_sync(0xFFFFFFFFu, ll, l), d = __shfl_sync(0xFFFFFFFFu, o_lit, l), sp = __shfl_sync(0xFFFFFFFFu, le_prev, l);
-                    if (blk.lit_kind == 1) zk_warp_fill(out + d, blk.lit_byte, n, lane);
-                    else zk_warp_copy(out + d, lit + sp, n, lane);
+                {
+                    // short runs byte-parallel; long runs with the vectorised warp copy
+                    uint32_t longlit = __ballot_sync(0xFFFFFFFFu, valid && ll >= 256);
+                    if (!longlit) zk_chunk_literals<false>(rg, lit, blk.lit_kind, blk.lit_byte, le, le_prev, o_lit, lane);
+                    else {
+                        if (valid && ll < 256) {
+                            uint8_t* d = out + o_lit;
+                            if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) d[i] = blk.lit_byte;
+                            else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) d[i] = sp[i]; }
+                        }
+                        while (longlit) {
+                            int l = __ffs((int)longlit) - 1; longlit &= longlit - 1;
+                            uint32_t n = __shfl_sync(0xFFFFFFFFu, ll, l), d = __shfl_sync(0xFFFFFFFFu, o_lit, l), sp = __shfl_sync(0xFFFFFFFFu, le_prev, l);
+                            if (blk.lit_kind == 1) zk_warp_fill(out + d, blk.lit_byte, n, lane);
+                            else zk_warp_copy(out + d, lit + sp, n, lane);
+                        }
+                    }
                 }
                 __syncwarp();
                 const uint32_t need_end = md - off + (ml < off ? ml : off);
@@ -876,24 +1034,21 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                     pending &= ~rmask;
                 }
                 zk_ring_reload(rg, chunk_end - half, chunk_end, lane, 32);
-                zk_d2_publish(sm, c, chunk_end, lane);
-                zk_d2_publish_flushed(sm, c, chunk_end, lane);
+                zk_d2_mark_done(sm, c, lane);
+                zk_d2_mark_flushed(sm, c, lane);
                 continue;
             }
 
             // ======== normal chunk: build the output in the ring, then flush
             // literal runs: no dependencies (HBM scratch -> ring)
-            if (valid && ll < ZK_LONG) {
-                if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) rg.at(o_lit + i) = blk.lit_byte;
-                else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) rg.at(o_lit + i) = sp[i]; }
-            }
-            uint32_t longlit = __ballot_sync(0xFFFFFFFFu, valid && ll >= ZK_LONG);
-            while (longlit) {
-                int l = __ffs((int)longlit) - 1; longlit &= longlit - 1;
-                uint32_t n = __shfl_sync(0xFFFFFFFFu, ll, l), d = __shfl_sync(0xFFFFFFFFu, o_lit, l), sp = __shfl_sync(0xFFFFFFFFu, le_prev, l);
-                for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = blk.lit_kind == 1 ? blk.lit_byte : lit[sp + i];
+            zk_chunk_literals<true>(rg, lit, blk.lit_kind, blk.lit_byte, le, le_prev, o_lit, lane);
+            {   // all literal runs are in place: sequences without a match (and the lanes past the last one) are complete
+                const uint32_t withm = __ballot_sync(0xFFFFFFFFu, valid && ml > 0);
+                zk_d2_progress(sm, c, ~withm, lane);
+                if (lane == 0) ZK_VOL(sm.litdone[c & (ZK_D2_META - 1)]) = c + 1;
             }
             __syncwarp();
+            ZK_STAMP(3);
 
             // matches.  near: the whole source is still resident in the ring (distance < R/2 from the chunk start);
             // far: it is read from HBM and must be published (done_pos).  A lane may go once its source is final.
@@ -902,26 +1057,91 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
             const uint32_t need_end = src0 + (ml < off ? ml : off);
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, valid && ml > 0);
             bool aborted = false;
-            while (pending) {
-                // lane 0 samples the pipeline state; everything below is warp-uniform
-                uint32_t dc = 0, dp = 0, fp = 0, ab = 0;
-                if (lane == 0) { dc = sm.done_chunk; dp = sm.done_pos; fp = sm.flushed_pos; ab = sm.abort_code != 0; __threadfence_block(); }
-                dc = __shfl_sync(0xFFFFFFFFu, dc, 0); dp = __shfl_sync(0xFFFFFFFFu, dp, 0); fp = __shfl_sync(0xFFFFFFFFu, fp, 0);
-                ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
-                __syncwarp();                      // orders the other lanes' data reads after lane 0's acquire
-                if (ab) { aborted = true; break; }
-                const bool oldest = dc == c;
-                const int first = __ffs((int)pending) - 1;
-                const uint32_t md_first = __shfl_sync(0xFFFFFFFFu, md, first);
-                const uint32_t frontier = oldest ? md_first : dp;        // bytes below it are final in the ring
+            // dataflow readiness: a match may go as soon as the bytes of its source are final -- the part that lies before this
+            // chunk is tracked per chunk (descriptors in shared memory), the part inside this chunk by lane order.  Sources older
+            // than R/2 are in HBM by construction of the start rule (flushed_pos >= chunk_end - R/2 > any far source).
+            // Step 1 (once): which in-flight chunks [klo, khi] produce my source?  Step 2 (poll): are they done?  The poll loop is
+            // the critical link of the frame's dependency chain, so it only reads those few flags.
+            uint32_t klo = 1, khi = 0;                                  // empty range: nothing to wait for outside this chunk
+            uint32_t mask_lo = 0, mask_hi = 0;                          // which sequences of chunk klo / khi produce my source
+            {
+                bool resolved = !(valid && ml > 0) || !near_src || src0 >= chunk_start;
+                const uint32_t ne = need_end < chunk_start ? need_end : chunk_start;
+                for (;;) {
+                    if (!resolved) {
+                        // chunk ids are consecutive and their start positions increase with the id: two binary searches over
+                        // the in-flight chunks [dc, c) find the chunks holding src0 and ne-1 (a linear walk cost one shared-memory
+                        // round trip per chunk of distance and dominated the kernel)
+                        const uint32_t dp = ZK_VOL(sm.done_pos), dc = ZK_VOL(sm.done_chunk);
+                        if (ne <= dp || dc >= c) { resolved = true; klo = 1; khi = 0; }
+                        else {
+                            bool ok = true;
+                            uint32_t lo = dc, hi = c - 1;                       // khi = largest k with start[k] < ne (start[dc] == done_pos < ne)
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi + 1) >> 1, e = mid & (ZK_D2_META - 1);
+                                if (ZK_VOL(sm.started[e]) != mid + 1) { ok = false; break; }
+                                if (ZK_VOL(sm.start[e]) < ne) lo = mid; else hi = mid - 1;
+                            }
+                            const uint32_t kh = lo;
+                            lo = dc; hi = kh;                                   // klo = largest k <= khi with start[k] <= src0, else dc
+                            while (ok && lo < hi) {
+                                const uint32_t mid = (lo + hi + 1) >> 1, e = mid & (ZK_D2_META - 1);
+                                if (ZK_VOL(sm.started[e]) != mid + 1) { ok = false; break; }
+                                if (ZK_VOL(sm.start[e]) <= src0) lo = mid; else hi = mid - 1;
+                            }
+                            const uint32_t kl = lo;
+                            if (ok && (ZK_VOL(sm.started[kl & (ZK_D2_META - 1)]) != kl + 1 || ZK_VOL(sm.started[kh & (ZK_D2_META - 1)]) != kh + 1)) ok = false;
+                            if (ok) {
+                                resolved = true; klo = kl; khi = kh;
+                                // first sequence of klo whose end lies beyond src0; last sequence of khi that starts before ne
+                                int a = 0, b = 0;
+                                { const uint32_t e = klo & (ZK_D2_META - 1); int lo2 = 0, hi2 = 31;
+                                  for (int st = 0; st < 5; st++) { int mid = (lo2 + hi2) >> 1; if (ZK_VOL(sm.oe[e][mid]) > src0) hi2 = mid; else lo2 = mid + 1; } a = lo2; }
+                                { const uint32_t e = khi & (ZK_D2_META - 1); int lo2 = 0, hi2 = 31;
+                                  for (int st = 0; st < 5; st++) { int mid = (lo2 + hi2) >> 1; if (ZK_VOL(sm.oe[e][mid]) >= ne) hi2 = mid; else lo2 = mid + 1; } b = lo2; }
+                                mask_lo = 0xFFFFFFFFu << a;
+                                mask_hi = b >= 31 ? 0xFFFFFFFFu : ((2u << b) - 1u);
+                                if (klo == khi) { mask_lo &= mask_hi; mask_hi = mask_lo; }
+                            }
+                        }
+                    }
+                    if (__all_sync(0xFFFFFFFFu, resolved)) break;
+                    if (zk_d2_aborted(sm)) { aborted = true; break; }
+                    ZK_SPIN();
+                }
+            }
+            ZK_STAMP(4);
+            bool stamped5 = false;
+            while (pending && !aborted) {
                 const bool mine = (pending >> lane) & 1;
-                // near sources come from the ring (final is enough); far sources from HBM (must be flushed)
-                const bool ready = mine && (near_src ? (need_end <= frontier || (oldest && lane == first)) : need_end <= fp);
+                bool ext_ok = true;
+                if (mine && khi >= klo) {
+                    const uint32_t dc = ZK_VOL(sm.done_chunk);
+                    for (uint32_t k = khi + 1; k-- > klo;) {
+                        if (k < dc) break;                                                   // it and everything older is done
+                        const uint32_t e = k & (ZK_D2_META - 1);
+                        const uint32_t need = k == khi ? mask_hi : (k == klo ? mask_lo : 0xFFFFFFFFu);
+                        if (ZK_VOL(sm.started[e]) != k + 1 || ZK_VOL(sm.litdone[e]) != k + 1 || (ZK_VOL(sm.dmask[e]) & need) != need) { ext_ok = false; break; }
+                    }
+                    if (ext_ok) khi = 0, klo = 1;                       // sticky
+                }
+                const int first = __ffs((int)pending) - 1;
+                const uint32_t md_first = __shfl_sync(0xFFFFFFFFu, md, first);   // inside this chunk everything below it is final
+                const bool ready = mine && ext_ok && (need_end <= md_first || lane == first);
                 const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, ready);
-                if (!rmask) { ZK_SPIN(); continue; }
+                if (!rmask) { if (zk_d2_aborted(sm)) { aborted = true; break; } ZK_SPIN(); continue; }
+                __threadfence_block();             // acquire: the flags were read before the data is
+                if (!stamped5) { ZK_STAMP(5); stamped5 = true; }
                 if (ready && ml < ZK_LONG) {
-                    if (near_src) for (uint32_t i = 0; i < ml; i++) rg.at(md + i) = rg.at(src0 + i);
-                    else { const uint8_t* sp = out + src0; for (uint32_t i = 0; i < ml; i++) rg.at(md + i) = sp[i]; }
+                    if (near_src) rg.copy_near(md, src0, ml);
+                    else {   // far source (HBM, never overlapping): 8 bytes per round trip
+                        const uint8_t* sp = out + src0;
+                        for (uint32_t i = 0; i < ml; i += 8) {
+                            unsigned long long v = zk_ld8_unaligned(sp + i);
+                            const uint32_t nb = ml - i < 8 ? ml - i : 8;
+                            for (uint32_t q = 0; q < nb; q++) { rg.at(md + i + q) = (uint8_t)v; v >>= 8; }
+                        }
+                    }
                 }
                 uint32_t longm = __ballot_sync(0xFFFFFFFFu, ready && ml >= ZK_LONG);
                 while (longm) {
@@ -936,13 +1156,16 @@ __global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t r
                         for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = rg.at(d - o + (i % o));
                     }
                 }
+                zk_d2_progress(sm, c, rmask, lane);    // dependants of these sequences may go now (not only when the whole chunk is done)
                 __syncwarp();
                 pending &= ~rmask;
             }
             if (aborted) break;
-            zk_d2_publish(sm, c, chunk_end, lane);                 // dependants can read the ring now ...
+            ZK_STAMP(6);
+            zk_d2_mark_done(sm, c, lane);                          // dependants can read the ring now ...
+            ZK_STAMP(7);
             zk_ring_flush(rg, chunk_start, chunk_end, lane);       // ... while the HBM flush happens off the critical chain
-            zk_d2_publish_flushed(sm, c, chunk_end, lane);
+            zk_d2_mark_flushed(sm, c, lane);
         }
         // advance to the next block
         if (has_seq) {
@@ -1143,6 +1366,14 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     a.lit = ws->lit; a.seq_lit_end = ws->seq_lit_end; a.seq_out_end = ws->seq_out_end; a.seq_off = ws->seq_off;
     a.huf_list = ws->huf_list; a.seq_list = ws->seq_list;
     a.cap_blocks = ws->cap_blocks; a.cap_lit = ws->cap_lit - 64; a.cap_seq = ws->cap_seq;
+    a.trace = nullptr;
+#ifndef ZK_EMUL
+    if (getenv("ZK_EXEC_TRACE")) {
+        if (!ws->trace) cudaMalloc((void**)&ws->trace, 1024 * 8 * 8);
+        cudaMemsetAsync(ws->trace, 0, 1024 * 8 * 8, stream);
+        a.trace = ws->trace;
+    }
+#endif
     ws->prof.begin(0, stream);
     ZK_LAUNCH(zk_scan_kernel, (n + 127) / 128, 128, 0, stream, a);
     ws->prof.end(0, stream);
@@ -1181,7 +1412,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     // (`share` > 1: that many sub-batches of a host pipeline run concurrently on different streams)
     int per_sm = (int)(((unsigned long long)n * (unsigned)(ws->share > 0 ? ws->share : 1) + (uint32_t)sms - 1) / (uint32_t)sms);
     int W = exec_warps;
-    if (W <= 0) { W = 16 / per_sm; if (W < 1) W = 1; }
+    if (W <= 0) { W = 32 / per_sm; if (W < 2) W = 2; }     // measured on B200: 16 warps for <= 148 entries, 8 for ~512, 2 for thousands
     if (W > 16) W = 16;
     uint32_t ring = 128 * 1024;
     while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;
@@ -1207,6 +1438,13 @@ int zk_decode_collect(ZkDecodeWs* ws, cudaStream_t stream, int32_t* status_out) 
     if (cudaGetLastError() != cudaSuccess) return -(int)ZKZ_GENERIC;
 #endif
     ws->pending_n = 0;
+#ifndef ZK_EMUL
+    if (ws->trace && getenv("ZK_EXEC_TRACE")) {
+        static unsigned long long host[1024 * 8];
+        cudaMemcpy(host, ws->trace, sizeof host, cudaMemcpyDeviceToHost);
+        FILE* f = fopen(getenv("ZK_EXEC_TRACE"), "wb"); if (f) { fwrite(host, 1, sizeof host, f); fclose(f); }
+    }
+#endif
     ws->prof.harvest();
     if (ws->h_counters->overflow) {
         ws->want_blocks = (size_t)ws->h_counters->n_blocks; ws->want_lit = (size_t)ws->h_counters->n_lit; ws->want_seq = (size_t)ws->h_counters->n_seq;

@@ -13,6 +13,7 @@ struct ZkDecodeArgs {                 // kernel parameter block (by value)
     uint8_t* lit; uint32_t* seq_lit_end; uint32_t* seq_out_end; uint32_t* seq_off;
     uint32_t* huf_list; uint32_t* seq_list;   // compacted indices of blocks with Huffman literals / with sequences
     unsigned long long cap_blocks, cap_lit, cap_seq;
+    unsigned long long* trace;        // debug: per-chunk clock64 stamps of entry 0 (env ZK_EXEC_TRACE), else nullptr
 };
 
 struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on demand, reused across batches
@@ -25,6 +26,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
     bool attr_set = false; uint32_t ring_override = 0;
     uint32_t huf_pad = 0;             // extra dynamic smem per Huffman CTA: fewer resident CTAs -> more L1 for the streams (tuning)
+    unsigned long long* trace = nullptr;
     int share = 1;                    // how many batches share the GPU concurrently (host pipeline depth)
     cudaStream_t side = nullptr; cudaEvent_t ev_scan = nullptr, ev_huf = nullptr;   // Huffman kernel runs beside the FSE kernel
     ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
