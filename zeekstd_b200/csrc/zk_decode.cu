@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(128) zk_scan_kernel(ZkDecodeArgs a) {
 // here every lane of a warp runs the identical decode loop over ITS OWN block with ITS OWN tables
 // in shared memory, so one issued instruction advances up to ZK_SEQ_LANES chains.
 // =============================================================================================
-#define ZK_SEQ_LANES 9            // 9 x 11.7 KiB of tables per warp-CTA -> 2 CTAs / SM
+#define ZK_SEQ_LPW 3              // chains per warp
+#define ZK_SEQ_WARPS 3            // warps per CTA: the same 9 x 11.7 KiB of tables per CTA (2 CTAs / SM) spread over more warps --
+#define ZK_SEQ_LANES (ZK_SEQ_LPW * ZK_SEQ_WARPS)   // each chain is ALU-latency bound, so more warps per SM hide more of it
 
 struct ZkSeqSlot {
     ZkSeqCell ll[512], ml[512], of[256];       // 10 KiB
@@ -373,24 +375,24 @@ __device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkDecodeArgs& a, c
     return st;
 }
 
-__global__ void __launch_bounds__(32) zk_seq_kernel(ZkDecodeArgs a) {
+__global__ void __launch_bounds__(32 * ZK_SEQ_WARPS) zk_seq_kernel(ZkDecodeArgs a) {
     ZK_DYN_SMEM(smem);
     ZkSeqSlot* slots = (ZkSeqSlot*)smem;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.counters->overflow) return;
     const uint32_t n = a.counters->n_seq_blocks;
-    for (;;) {
+    for (;;) {                                  // every warp pulls its own groups of ZK_SEQ_LPW blocks
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(&a.work_counter[0], 1u);
         g = __shfl_sync(0xFFFFFFFFu, g, 0);
-        uint32_t first = g * ZK_SEQ_LANES;
+        uint32_t first = g * ZK_SEQ_LPW;
         if (first >= n) break;
         uint32_t my = first + lane;
-        if (lane < ZK_SEQ_LANES && my < n) {
+        if (lane < ZK_SEQ_LPW && my < n) {
             uint32_t bidx = a.seq_list[my];
             ZkBlock blk = a.blocks[bidx];
             if (a.entries[blk.entry].status == 0) {
-                int st = zk_decode_block_sequences(slots[lane], a, blk, bidx, a.comp + a.c_off[blk.entry]);
+                int st = zk_decode_block_sequences(slots[warp * ZK_SEQ_LPW + lane], a, blk, bidx, a.comp + a.c_off[blk.entry]);
                 a.blocks[bidx].status = st ? -st : 0;
             }
         }
@@ -1403,7 +1405,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     ws->prof.end(2, ws->side);
     ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, ws->side));
     ws->prof.begin(1, stream);
-    ZK_LAUNCH(zk_seq_kernel, gs, 32, seq_smem, stream, a);
+    ZK_LAUNCH(zk_seq_kernel, gs, 32 * ZK_SEQ_WARPS, seq_smem, stream, a);
     ws->prof.end(1, stream);
     ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_huf, 0));
     // exec stage: ring size / warps per entry chosen from how many entries share the machine

@@ -347,7 +347,9 @@ __device__ void zkc_fse_set_predefined(ZkcFse& t, int which) {
 // written to a per-block scratch ([0,256) header + table descriptions, [256,..) bitstream) and moved into place by
 // the literal/assembly kernel.
 // =============================================================================================
-#define ZKC_SEQ_LANES 16
+#define ZKC_SEQ_LPW 4              // chains per warp
+#define ZKC_SEQ_WARPS 4            // warps per CTA (same 16 tables per CTA; more warps hide the ALU latency of each chain)
+#define ZKC_SEQ_LANES (ZKC_SEQ_LPW * ZKC_SEQ_WARPS)
 struct ZkcSeqSlot { ZkcFse fse[3]; uint32_t cnt[3][64]; uint8_t symof[512]; };
 struct ZkcTabs { uint32_t ll_base[36], ml_base[53]; uint8_t ll_bits[36], ml_bits[53], ll_code[64], ml_code[128]; };
 __device__ __forceinline__ uint32_t zkc_llc(const ZkcTabs& tb, uint32_t ll) { return ll < 64 ? tb.ll_code[ll] : (uint32_t)zk_highbit(ll) + 19; }
@@ -481,22 +483,22 @@ __device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const ui
     return true;
 }
 
-__global__ void __launch_bounds__(32) zk_seq_enc_kernel(ZkEncodeArgs a) {
+__global__ void __launch_bounds__(32 * ZKC_SEQ_WARPS) zk_seq_enc_kernel(ZkEncodeArgs a) {
     ZK_DYN_SMEM(smem);
     ZkcTabs* tb = (ZkcTabs*)smem;
     ZkcSeqSlot* slots = (ZkcSeqSlot*)(smem + ((sizeof(ZkcTabs) + 15) & ~(size_t)15));
-    const int lane = threadIdx.x;
-    for (int i = lane; i < 36; i += 32) { tb->ll_base[i] = ZK_LL_BASE[i]; tb->ll_bits[i] = ZK_LL_BITS[i]; }
-    for (int i = lane; i < 53; i += 32) { tb->ml_base[i] = ZK_ML_BASE[i]; tb->ml_bits[i] = ZK_ML_BITS[i]; }
-    for (int i = lane; i < 64; i += 32) tb->ll_code[i] = ZKC_LL_CODE[i];
-    for (int i = lane; i < 128; i += 32) tb->ml_code[i] = ZKC_ML_CODE[i];
-    __syncwarp();
-    const uint32_t b = blockIdx.x * ZKC_SEQ_LANES + lane;
-    if (lane < ZKC_SEQ_LANES && b < a.n_blocks) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, nt = 32 * ZKC_SEQ_WARPS;
+    for (int i = tid; i < 36; i += nt) { tb->ll_base[i] = ZK_LL_BASE[i]; tb->ll_bits[i] = ZK_LL_BITS[i]; }
+    for (int i = tid; i < 53; i += nt) { tb->ml_base[i] = ZK_ML_BASE[i]; tb->ml_bits[i] = ZK_ML_BITS[i]; }
+    for (int i = tid; i < 64; i += nt) tb->ll_code[i] = ZKC_LL_CODE[i];
+    for (int i = tid; i < 128; i += nt) tb->ml_code[i] = ZKC_ML_CODE[i];
+    __syncthreads();
+    const uint32_t b = (blockIdx.x * ZKC_SEQ_WARPS + warp) * ZKC_SEQ_LPW + lane;
+    if (lane < ZKC_SEQ_LPW && b < a.n_blocks) {
         const uint32_t nseq = a.blocks[b].nseq;
         uint32_t hb = 0, sb = 0;
         if (nseq) {
-            const bool ok = zkc_encode_sequences(slots[lane], *tb, a.seq_ll + (size_t)b * ZKC_MAXSEQ, a.seq_ml + (size_t)b * ZKC_MAXSEQ,
+            const bool ok = zkc_encode_sequences(slots[warp * ZKC_SEQ_LPW + lane], *tb, a.seq_ll + (size_t)b * ZKC_MAXSEQ, a.seq_ml + (size_t)b * ZKC_MAXSEQ,
                                                  a.seq_off + (size_t)b * ZKC_MAXSEQ, nseq, b % a.blocks_per_frame == 0, a.seqsec + (size_t)b * ZKC_SEQSEC, &hb, &sb);
             if (!ok) { hb = 0; sb = 0; }
         }
@@ -1014,7 +1016,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ws->prof.begin(6, stream);
     ZKC_CUDA_OK(cudaEventRecord(ws->ev_a, stream));
     ZKC_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_a, 0));
-    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SEQ_LANES - 1) / ZKC_SEQ_LANES), 32, seq_smem, ws->side, a);
+    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SEQ_LANES - 1) / ZKC_SEQ_LANES), 32 * ZKC_SEQ_WARPS, seq_smem, ws->side, a);
     ZKC_CUDA_OK(cudaEventRecord(ws->ev_b, ws->side));
     ZK_LAUNCH(zk_lit_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
     ZKC_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_b, 0));
