@@ -865,7 +865,7 @@ __device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint3
     }
 }
 
-__global__ void __launch_bounds__(512) zk_exec_kernel(ZkDecodeArgs a, uint32_t ring_bytes) {
+__global__ void __launch_bounds__(512, 1) zk_exec_kernel(ZkDecodeArgs a, uint32_t ring_bytes) {
     __shared__ ZkD2Smem sm;
     ZK_DYN_SMEM(ring_mem);
     const uint32_t e = blockIdx.x;
