@@ -1414,7 +1414,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     // (`share` > 1: that many sub-batches of a host pipeline run concurrently on different streams)
     int per_sm = (int)(((unsigned long long)n * (unsigned)(ws->share > 0 ? ws->share : 1) + (uint32_t)sms - 1) / (uint32_t)sms);
     int W = exec_warps;
-    if (W <= 0) { W = 32 / per_sm; if (W < 2) W = 2; }     // measured on B200: 16 warps for <= 148 entries, 8 for ~512, 2 for thousands
+    if (W <= 0) { W = 18 / per_sm; if (W < 2) W = 2; }     // 113 registers/thread -> 18 warps per SM: keep every entry of the batch resident
     if (W > 16) W = 16;
     uint32_t ring = 128 * 1024;
     while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;

@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
                 nlit += ll; nseq++;
                 anchor = mpos + ml; rep = off;
                 const size_t rel = anchor - wb;
-                next_lane = rel >= 32u * stride ? 32u : (uint32_t)((rel + stride - 1) / stride);
+                // ceil(rel / stride) without an integer division (stride is 1..4)
+                next_lane = rel >= 32u * stride ? 32u
+                          : (stride == 1 ? (uint32_t)rel : (stride == 2 ? (uint32_t)((rel + 1) >> 1) : (stride == 4 ? (uint32_t)((rel + 3) >> 2) : (uint32_t)(((rel + 2) * 43691u) >> 17))));
             }
             ip = anchor > wb + 32u * stride ? anchor : wb + 32u * stride;
         }
@@ -222,17 +224,19 @@ typedef ZkcBitWT<false> ZkcBitW;
 typedef ZkcBitWT<true> ZkcBitWW;
 
 // FSE compression table for one symbol alphabet (state values in [S, 2S))
+// (table logs are capped at 8 by this encoder: 1 KiB per table lets twice as many block chains share an SM's shared memory)
 struct ZkcFse {
-    uint16_t state_tbl[512];
-    int32_t delta_find[64];
+    uint16_t state_tbl[256];
     uint32_t delta_nb[64];
+    int16_t delta_find[64];
     int16_t norm[64];
-    int log, nsym, mode;                 // mode: 0 predefined, 1 RLE, 2 FSE-compressed
-    uint32_t rle_sym;
+    int8_t log, mode;                    // mode: 0 predefined, 1 RLE, 2 FSE-compressed
+    uint8_t nsym, rle_sym;
 };
 
 // normalise counts to a sum of 2^log with every present symbol >= 1 (any such distribution is a valid header)
-__device__ void zkc_fse_normalize(ZkcFse& t, const uint32_t* cnt, int nsym, uint32_t total, int log) {
+template <class CT>
+__device__ void zkc_fse_normalize(ZkcFse& t, const CT* cnt, int nsym, uint32_t total, int log) {
     const uint32_t S = 1u << log;
     uint32_t sum = 0, best = 0; int besti = 0;
     for (int s = 0; s < nsym; s++) {
@@ -254,7 +258,7 @@ __device__ void zkc_fse_normalize(ZkcFse& t, const uint32_t* cnt, int nsym, uint
             t.norm[bi] = (int16_t)(bv - take); sum -= take;
         }
     }
-    t.log = log; t.nsym = nsym;
+    t.log = (int8_t)log; t.nsym = (uint8_t)nsym;
 }
 
 // build the encoding tables from t.norm (mirror of A.6 table build)
@@ -275,12 +279,12 @@ __device__ void zkc_fse_build(ZkcFse& t, uint8_t* symof /* >= 512 bytes scratch 
     for (int s = 0; s < nsym; s++) {
         int n = t.norm[s];
         if (n == 0) { t.delta_nb[s] = ((uint32_t)(log + 1) << 16) - (1u << log); t.delta_find[s] = 0; }
-        else if (n == 1 || n == -1) { t.delta_nb[s] = ((uint32_t)log << 16) - (1u << log); t.delta_find[s] = total - 1; total++; }
+        else if (n == 1 || n == -1) { t.delta_nb[s] = ((uint32_t)log << 16) - (1u << log); t.delta_find[s] = (int16_t)(total - 1); total++; }
         else {
             uint32_t max_bits_out = (uint32_t)log - (uint32_t)zk_highbit((uint32_t)n - 1);
             uint32_t min_state_plus = (uint32_t)n << max_bits_out;
             t.delta_nb[s] = (max_bits_out << 16) - min_state_plus;
-            t.delta_find[s] = total - n; total += n;
+            t.delta_find[s] = (int16_t)(total - n); total += n;
         }
     }
 }
@@ -350,7 +354,7 @@ __device__ void zkc_fse_set_predefined(ZkcFse& t, int which) {
 #define ZKC_SEQ_LPW 4              // chains per warp
 #define ZKC_SEQ_WARPS 4            // warps per CTA (same 16 tables per CTA; more warps hide the ALU latency of each chain)
 #define ZKC_SEQ_LANES (ZKC_SEQ_LPW * ZKC_SEQ_WARPS)
-struct ZkcSeqSlot { ZkcFse fse[3]; uint32_t cnt[3][64]; uint8_t symof[512]; };
+struct ZkcSeqSlot { ZkcFse fse[3]; uint16_t cnt[3][64]; uint8_t symof[256]; };
 struct ZkcTabs { uint32_t ll_base[36], ml_base[53]; uint8_t ll_bits[36], ml_bits[53], ll_code[64], ml_code[128]; };
 __device__ __forceinline__ uint32_t zkc_llc(const ZkcTabs& tb, uint32_t ll) { return ll < 64 ? tb.ll_code[ll] : (uint32_t)zk_highbit(ll) + 19; }
 __device__ __forceinline__ uint32_t zkc_mlc(const ZkcTabs& tb, uint32_t mlb) { return mlb < 128 ? tb.ml_code[mlb] : (uint32_t)zk_highbit(mlb) + 36; }
@@ -382,7 +386,7 @@ __device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const ui
     // three code histograms are counted.  Blocks are coded independently, so repeat codes are used only once three explicit
     // offsets have been coded in this block (the decoder's history is then certain); the first block of a frame starts from
     // the known {1,4,8}.
-    for (int i = 0; i < 3 * 64; i++) (&sl.cnt[0][0])[i] = 0;
+    for (int i = 0; i < 3 * 64; i++) (&sl.cnt[0][0])[i] = 0;          // (u16 counters: a block has at most 8192 sequences)
     {
         uint32_t r0 = 1, r1 = 4, r2 = 8, known = first_block ? 3 : 0;
         ZkcSeq8 cur, nxt;
@@ -425,10 +429,10 @@ __device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const ui
     uint32_t modes = 0;
     for (int t = 0; t < 3; t++) {
         ZkcFse& ft = sl.fse[t];
-        const int max_log = t == 1 ? 8 : 9, nsym_all = t == 0 ? 36 : (t == 1 ? 32 : 53);
+        const int max_log = 8, nsym_all = t == 0 ? 36 : (t == 1 ? 32 : 53);
         int last = nsym_all - 1; while (last > 0 && sl.cnt[t][last] == 0) last--;
         uint32_t distinct = 0; for (int q = 0; q <= last; q++) distinct += sl.cnt[t][q] != 0;
-        if (distinct == 1) { ft.mode = 1; ft.rle_sym = (uint32_t)last; ft.log = 0; out[hp++] = (uint8_t)last; modes |= 1u << (6 - 2 * t); }
+        if (distinct == 1) { ft.mode = 1; ft.rle_sym = (uint8_t)last; ft.log = 0; out[hp++] = (uint8_t)last; modes |= 1u << (6 - 2 * t); }
         else if (nseq < 48 && (t != 1 || last <= 28)) { zkc_fse_set_predefined(ft, t); zkc_fse_build(ft, sl.symof); }
         else {
             int lg = zk_highbit(nseq) - 1; if (lg < 5) lg = 5; if (lg > max_log) lg = max_log;
@@ -624,10 +628,13 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
             // canonical codes exactly as the decoder lays out its table: weight ascending, symbol ascending (A.4)
             if (lane == 0) {
                 int last_sym = 255; while (last_sym > 0 && sm.hlen[last_sym] == 0) last_sym--;
-                uint32_t pos = 0;
-                for (int w = 1; w <= maxlen; w++)
-                    for (int s = 0; s <= last_sym; s++)
-                        if (sm.hlen[s] && maxlen + 1 - sm.hlen[s] == w) { sm.hcode[s] = (uint16_t)(pos >> (w - 1)); pos += 1u << (w - 1); }
+                // start cell of every symbol in two linear passes: cells per weight class, then a running cursor per class
+                uint32_t cls[13];
+                for (int w = 0; w < 13; w++) cls[w] = 0;
+                for (int s = 0; s <= last_sym; s++) if (sm.hlen[s]) cls[maxlen + 1 - sm.hlen[s]] += 1;
+                { uint32_t acc = 0; for (int w = 1; w <= maxlen; w++) { uint32_t n = cls[w]; cls[w] = acc; acc += n << (w - 1); } }
+                for (int s = 0; s <= last_sym; s++)
+                    if (sm.hlen[s]) { const int w = maxlen + 1 - sm.hlen[s]; sm.hcode[s] = (uint16_t)(cls[w] >> (w - 1)); cls[w] += 1u << (w - 1); }
                 // tree description: weights of symbols 0..last_sym-1 (the last one is implied)
                 int nw = last_sym;
                 for (int s = 0; s < nw; s++) sm.weights[s] = sm.hlen[s] ? (uint8_t)(maxlen + 1 - sm.hlen[s]) : 0;
