@@ -3,6 +3,7 @@
 // top of these entry points only.
 #include "zk_ctx.h"
 #include "../../include/zeekstd_b200.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <vector>
 
@@ -19,7 +20,7 @@ static size_t zk_env_size(const char* name, size_t dflt) {
     return (size_t)strtoull(s, nullptr, 10);
 }
 
-static int zk_host_slots() { size_t v = zk_env_size("ZK_HOST_SLOTS", 4); return (int)(v < 1 ? 1 : (v > ZK_SLOTS ? ZK_SLOTS : v)); }
+static int zk_host_slots() { size_t v = zk_env_size("ZK_HOST_SLOTS", 6); return (int)(v < 1 ? 1 : (v > ZK_SLOTS ? ZK_SLOTS : v)); }
 
 extern "C" const char* zk_version(void) {
 #ifdef ZK_EMUL
@@ -86,8 +87,15 @@ extern "C" int32_t zk_ctx_create(int32_t device_ordinal, uint32_t flags, zk_ctx*
     zk_ctx* c = new zk_ctx();
     c->device = device_ordinal;
     c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    // ZK_HOST_PRIO (default 1): slot i runs at stream priority (greatest + i): concurrent sub-batches of the host pipelines then
+    // complete staggered (oldest slot first) instead of all at once, which keeps the D2H engine busy from early on
+    int least = 0, greatest = 0;
+    const bool use_prio = zk_env_size("ZK_HOST_PRIO", 1) != 0;
+    if (use_prio) cudaDeviceGetStreamPriorityRange(&least, &greatest);
     for (int i = 0; i < ZK_SLOTS; i++) {
-        if (cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZK_ERR_NO_DEVICE; }
+        const int prio = use_prio ? (greatest + i < least ? greatest + i : least) : 0;
+        if (cudaStreamCreateWithPriority(&c->slot[i].stream, cudaStreamNonBlocking, prio) != cudaSuccess) { delete c; return ZK_ERR_NO_DEVICE; }
+        c->slot[i].dws.prio = c->slot[i].ews.prio = prio;
         c->slot[i].dws.sm_count = c->sm_count;
         c->slot[i].dws.ring_override = (uint32_t)zk_env_size("ZK_RING_BYTES", 0);   // tuning / tests: power of two >= 1024
         c->slot[i].dws.huf_pad = (uint32_t)zk_env_size("ZK_HUF_PAD", 0);
@@ -170,10 +178,34 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
     return worst;
 }
 
+// ZK_E2E_TRACE=1: per-sub-batch timeline of the host-pointer paths (CUDA events on the slot streams), printed to stderr.
+struct ZkTrace {
+    bool on = false; cudaEvent_t t0 = nullptr; std::vector<cudaEvent_t> ev; std::vector<int> tag;
+    void begin(cudaStream_t st) {
+        on = getenv("ZK_E2E_TRACE") != nullptr; if (!on) return;
+        cudaEventCreate(&t0); cudaEventRecord(t0, st);
+    }
+    void mark(cudaStream_t st, int sub, int what) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(sub * 8 + what);
+    }
+    void end(const char* name) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        static const char* W[] = {"h2d0", "h2d1", "kern1", "d2h0", "d2h1"};
+        for (size_t i = 0; i < ev.size(); i++) {
+            float ms = 0; cudaEventElapsedTime(&ms, t0, ev[i]);
+            fprintf(stderr, "%s sub %d %s %.3f\n", name, tag[i] >> 3, W[tag[i] & 7], ms);
+            cudaEventDestroy(ev[i]);
+        }
+        cudaEventDestroy(t0);
+    }
+};
+
 struct ZkSubDec { uint32_t first = 0, count = 0; std::vector<uint64_t> c_rel, d_rel; bool busy = false; };
 
 static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
-                              uint8_t* dst, int verify) {
+                              uint8_t* dst, int verify, ZkTrace* tr = nullptr, int k = 0) {
     ZkSlot& s = c->slot[si];
     uint32_t f = sb.first, cnt = sb.count;
     size_t cbytes = (size_t)(c_off[f + cnt] - c_off[f]), obytes = (size_t)(d_off[f + cnt] - d_off[f]);
@@ -181,12 +213,16 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     if (rc) return rc;
     sb.c_rel.resize(cnt + 1); sb.d_rel.resize(cnt + 1);
     for (uint32_t j = 0; j <= cnt; j++) { sb.c_rel[j] = c_off[f + j] - c_off[f]; sb.d_rel[j] = d_off[f + j] - d_off[f]; }
+    if (tr) tr->mark(s.stream, k, 0);
     ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
-    s.dws.share = zk_host_slots();
+    if (tr) tr->mark(s.stream, k, 1);
+    s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", (size_t)(zk_host_slots() + 1) / 2);
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
     if (rc) return rc;
+    if (tr) tr->mark(s.stream, k, 2);
     if (obytes) ZK_RT_OK(cudaMemcpyAsync(dst + d_off[f], s.d_out, obytes, cudaMemcpyDeviceToHost, s.stream));
+    if (tr) tr->mark(s.stream, k, 4);
     sb.busy = true;
     return 0;
 }
@@ -211,18 +247,19 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
     if (!c || (n && (!comp || !c_off || !d_off || !dst))) return ZK_ERR_INVALID_ARG;
     if (n == 0) return 0;
     ZK_RT_OK(cudaSetDevice(c->device));
-    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)256 << 20);     // measured best on B200 (tools/e2e_sweep.py)
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);     // measured best on B200 (tools/e2e_sweep2.sh)
     ZkSubDec sub[ZK_SLOTS];
     const int NS = zk_host_slots();
     int32_t worst = 0;
     uint32_t k = 0;
+    ZkTrace tr; tr.begin(c->slot[0].stream);
     for (uint32_t first = 0; first < n; k++) {
         int si = (int)(k % NS);
         int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
         if (rc && !worst) worst = rc;
         uint32_t end = zk_next_sub(d_off, first, n, sub_bytes, 1u << 20);
         sub[si].first = first; sub[si].count = end - first;
-        rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify);
+        rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify, &tr, (int)k);
         if (rc) { if (!worst) worst = rc; break; }
         first = end;
     }
@@ -230,6 +267,7 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
         int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
         if (rc && !worst) worst = rc;
     }
+    tr.end("dec");
     return worst;
 }
 
@@ -288,13 +326,15 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
     const uint32_t nf = zk_frames_of(n, frame_size);
     if (nf > frames_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
     ZK_RT_OK(cudaSetDevice(c->device));
-    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES_ENC", (size_t)64 << 20);   // measured best on B200 (tools/e2e_sweep.py)
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES_ENC", (size_t)128 << 20);   // measured best on B200 (tools/e2e_sweep2.sh)
     uint32_t per = (uint32_t)(sub_bytes / frame_size); if (per == 0) per = 1;
     // The compressed size of a sub-batch is only known when it completes, so output positions are assigned in
     // order at completion time: H2D and kernels of later sub-batches overlap the D2H of earlier ones.
     ZkSubEnc sub[ZK_SLOTS];
     size_t out_pos = 0; int32_t err = 0;
     std::vector<uint32_t> tmp_sizes(per);
+    ZkTrace tr; tr.begin(c->slot[0].stream);
+    int sub_k[ZK_SLOTS] = {0};
     auto finish = [&](int si) -> int {
         ZkSubEnc& sb = sub[si]; ZkSlot& s = c->slot[si];
         if (!sb.busy) return 0;
@@ -303,7 +343,9 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         int rc = zk_encode_collect(&s.ews, s.stream, c_sizes ? c_sizes + sb.f0 : tmp_sizes.data(), &produced);
         if (rc) return rc;
         if (out_pos + produced > dst_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
+        tr.mark(s.stream, sub_k[si], 3);
         if (cudaMemcpyAsync(dst + out_pos, s.d_out, produced, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) return ZK_ERR_NO_DEVICE;
+        tr.mark(s.stream, sub_k[si], 4);
         out_pos += produced;
         return 0;
     };
@@ -324,9 +366,12 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         const size_t bound = zk_encode_bound(sb.in_len, frame_size);
         int rc = zk_slot_ensure(&s, sb.in_len + 32, bound + 32);
         if (rc) { err = rc; break; }
+        sub_k[si] = (int)k; tr.mark(s.stream, (int)k, 0);
         if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }
+        tr.mark(s.stream, (int)k, 1);
         rc = zk_encode_enqueue(&s.ews, s.stream, s.d_in, sb.in_len, frame_size, level, checksum, s.d_out, bound, sb.cnt);
         if (rc) { err = rc; break; }
+        tr.mark(s.stream, (int)k, 2);
         sb.busy = true; order[n_inflight++ % ZK_SLOTS] = si;
     }
     // drain in submission order
@@ -336,6 +381,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         if (rc) err = rc;
     }
     for (int si = 0; si < ZK_SLOTS; si++) cudaStreamSynchronize(c->slot[si].stream);
+    tr.end("enc");
     (void)order;
     if (err) return err;
     if (d_sizes) for (uint32_t f = 0; f < nf; f++) {

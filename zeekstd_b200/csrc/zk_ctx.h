@@ -4,7 +4,7 @@
 #include "zk_decode.h"
 #include "zk_encode.h"
 
-#define ZK_SLOTS 6                        // pipeline depth of the host<->device paths (H2D | kernels | D2H overlap)
+#define ZK_SLOTS 8                        // pipeline depth of the host<->device paths (H2D | kernels | D2H overlap)
 
 struct ZkSlot {
     cudaStream_t stream = nullptr;

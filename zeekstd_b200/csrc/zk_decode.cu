@@ -1394,7 +1394,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     if (need_h < gh) gh = (uint32_t)need_h;
     // the two entropy kernels are independent: run the Huffman one on a side stream
     if (!ws->side) {
-        ZK_CUDA_OK(cudaStreamCreateWithFlags(&ws->side, cudaStreamNonBlocking));
+        ZK_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
         ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_scan, cudaEventDisableTiming));
         ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_huf, cudaEventDisableTiming));
     }

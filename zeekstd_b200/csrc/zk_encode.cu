@@ -68,7 +68,14 @@ __device__ __forceinline__ uint32_t zkc_hash5(unsigned long long v) {
 }
 
 // =============================================================================================
-// K-C1: match finding.  One warp per block; lane i examines position ip + i.
+// K-C1: match finding.  One warp per block; lane i examines position ip + i * stride.
+//
+// Every position is a 32-bit offset from `base` (the start of the searchable history, < 64 KiB before the end of the
+// block), so the u16 hash table stores positions directly.  A window is always full (32 valid lanes): the last < 40
+// bytes of a block are left as literals.  Matches are only taken from stride-1 windows -- when a wider window (used
+// after runs of misses on incompressible data) sees a candidate, the window is simply redone at stride 1.  That makes
+// literal emission a per-window register operation: a byte that no selected match covers is written from the lane that
+// already holds it (ballot + popc rank), and sequences are staged one per lane and stored 32 at a time.
 // =============================================================================================
 #define ZKC_C1_WARPS 4
 
@@ -80,63 +87,84 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
     uint16_t* table = tables[warp];
     size_t lo, hi, fstart;
     zkc_block_range(a, b, lo, hi, fstart);
-    const uint8_t* src = a.src;
-    // history: up to one block of the same frame before `lo` is searchable (offsets < 64 KiB fit the u16 table)
+    // history: up to one block of the same frame before `lo` is searchable (positions < 64 KiB fit the u16 table)
     const size_t base = lo - fstart >= ZKC_BLOCK ? lo - ZKC_BLOCK : fstart;
+    const uint8_t* sb = a.src + base;
+    const uint32_t lo32 = (uint32_t)(lo - base), hi32 = (uint32_t)(hi - base);
     for (int i = lane; i < (1 << ZKC_HLOG); i += 32) table[i] = 0;
     __syncwarp();
-    const uint32_t len = (uint32_t)(hi - lo);
+    const uint32_t len = hi32 - lo32;
     uint16_t* o_ll = a.seq_ll + (size_t)b * ZKC_MAXSEQ; uint16_t* o_ml = a.seq_ml + (size_t)b * ZKC_MAXSEQ;
     uint32_t* o_off = a.seq_off + (size_t)b * ZKC_MAXSEQ;
     uint8_t* o_lit = a.lits + (size_t)b * ZKC_BLOCK;
     uint32_t nseq = 0, nlit = 0;
+    uint32_t ip = lo32;                                     // every literal byte below ip has been written to o_lit
     if (len >= 16) {
-        const size_t mflimit = hi - 8;                      // last position where 8 bytes can be read
+        const uint32_t mflimit = hi32 - 8;                  // last position where 8 bytes can be read
+        const uint32_t lt_mask = (1u << lane) - 1u;
         // pre-insert the history so matches can reach into the previous block
         if (a.level >= 2) {
-            for (size_t p0 = base; p0 < lo; p0 += 32) {
-                const size_t p = p0 + lane;
-                const uint32_t hh = p < lo ? zkc_hash5(zkc_ld8(src + p)) : (0xFFFF0000u | (uint32_t)lane);
+            for (uint32_t p0 = 0; p0 < lo32; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                const uint32_t hh = p < lo32 ? zkc_hash5(zkc_ld8(sb + p)) : (0xFFFF0000u | (uint32_t)lane);
                 const uint32_t same = __match_any_sync(0xFFFFFFFFu, hh);
-                if (p < lo && lane == 31 - __clz((int)same)) table[hh] = (uint16_t)(p - base);
+                if (p < lo32 && lane == 31 - __clz((int)same)) table[hh] = (uint16_t)p;
             }
             __syncwarp();
         }
-        size_t ip = lo, anchor = lo;
+        uint32_t anchor = lo32;
         uint32_t rep = 0;                                   // last emitted offset (0 = none)
         uint32_t misses = 0;                                // consecutive windows without a match: widen the stride (incompressible data)
-        while (ip < mflimit) {
+        uint32_t s_ll = 0, s_ml = 0, s_off = 0;             // staged sequence (slot nseq & 31 lives in that lane)
+        for (;;) {
             const uint32_t stride = 1u + min(misses >> 3, 3u);
-            const size_t wb = ip;
-            const size_t p = wb + (size_t)lane * stride;
-            const bool valid = p < mflimit;
-            unsigned long long cur = 0; uint32_t h = 0, cand = 0;
-            if (valid) { cur = zkc_ld8(src + p); h = zkc_hash5(cur); cand = table[h]; }
+            if (ip + 32u * stride > mflimit) {
+                if (stride == 1) break;
+                misses = 0; continue;                       // the tail may still fit a stride-1 window
+            }
+            const uint32_t wb = ip;
+            const uint32_t p = wb + (uint32_t)lane * stride;
+            if (lane < 2) zk_prefetch_l1(sb + min(wb + 256u + 128u * (uint32_t)lane, hi32 - 1u));
+            const unsigned long long cur = zkc_ld8(sb + p);
+            const uint32_t h = zkc_hash5(cur);
+            const uint32_t cand = table[h];
             __syncwarp();
             // several lanes may hash to the same slot: the highest position wins, as sequential insertion would leave it
             // (keeps the compressed bytes deterministic)
-            const uint32_t same = __match_any_sync(0xFFFFFFFFu, valid ? h : (0xFFFF0000u | (uint32_t)lane));
-            if (valid && lane == 31 - __clz((int)same)) table[h] = (uint16_t)(p - base);
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, h);
+            if (lane == 31 - __clz((int)same)) table[h] = (uint16_t)p;
             // candidate from the hash table, and the repeat-offset candidate
             uint32_t moff = 0, mlen0 = 0;
-            if (valid) {
-                size_t cp = base + cand;
-                if (cp < p) {
-                    unsigned long long x = zkc_ld8(src + cp) ^ cur;
-                    uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
-                    if (m >= ZKC_MINMATCH) { moff = (uint32_t)(p - cp); mlen0 = m; }
-                }
-                if (rep && p - fstart >= rep) {
-                    unsigned long long x = zkc_ld8(src + p - rep) ^ cur;
-                    uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
-                    if (m >= 4 && m + 1 >= mlen0) { moff = rep; mlen0 = m; }
-                }
+            if (cand < p) {
+                const unsigned long long x = zkc_ld8(sb + cand) ^ cur;
+                const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
+                if (m >= ZKC_MINMATCH) { moff = p - cand; mlen0 = m; }
+            }
+            if (rep && p >= rep) {
+                const unsigned long long x = zkc_ld8(sb + p - rep) ^ cur;
+                const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
+                if (m >= 4 && m + 1 >= mlen0) { moff = rep; mlen0 = m; }
             }
             const uint32_t found = __ballot_sync(0xFFFFFFFFu, mlen0 != 0);
-            if (!found) { ip = wb + 32u * stride; misses++; continue; }
+            if (stride > 1) {
+                if (found) { misses = 0; continue; }        // compressible again: redo this window at stride 1
+                // the whole window is literals, straight from the registers
+                uint8_t* o = o_lit + nlit + (uint32_t)lane * stride;
+                o[0] = (uint8_t)cur; o[1] = (uint8_t)(cur >> 8);
+                if (stride > 2) o[2] = (uint8_t)(cur >> 16);
+                if (stride > 3) o[3] = (uint8_t)(cur >> 24);
+                nlit += 32u * stride; ip = wb + 32u * stride; misses++;
+                continue;
+            }
+            if (!found) {
+                o_lit[nlit + lane] = (uint8_t)cur;
+                nlit += 32u; ip = wb + 32u; misses++;
+                continue;
+            }
             misses = 0;
             // take every non-overlapping match of this window, left to right (one memory round trip serves them all)
             uint32_t next_lane = 0;
+            bool cov = false;                               // this lane's byte is covered by a selected match
             while (next_lane < 32) {
                 const uint32_t m = found & (0xFFFFFFFFu << next_lane);
                 if (!m) break;
@@ -148,39 +176,43 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
                     if (ml2 > ml + 1) { f++; ml = ml2; }
                 }
                 const uint32_t off = __shfl_sync(0xFFFFFFFFu, moff, f);
-                const size_t mpos = wb + (size_t)f * stride;
+                const uint32_t mpos = wb + (uint32_t)f;
                 if (ml == 8) {
                     // extend cooperatively: lane k compares bytes [8 + 8k, 16 + 8k) of the match, 256 bytes a round
                     for (;;) {
-                        const size_t q = mpos + ml + (size_t)lane * 8;
+                        const uint32_t q = mpos + ml + (uint32_t)lane * 8u;
                         uint32_t eq = 8;
-                        if (q + 8 <= hi) { unsigned long long x = zkc_ld8(src + q) ^ zkc_ld8(src + q - off); if (x) eq = (uint32_t)(__ffsll((long long)x) - 1) >> 3; }
-                        else { eq = 0; for (size_t t = q; t < hi && src[t] == src[t - off]; t++) eq++; }
+                        if (q + 8 <= hi32) { const unsigned long long x = zkc_ld8(sb + q) ^ zkc_ld8(sb + q - off); if (x) eq = (uint32_t)(__ffsll((long long)x) - 1) >> 3; }
+                        else { eq = 0; for (uint32_t t = q; t < hi32 && sb[t] == sb[t - off]; t++) eq++; }
                         const uint32_t stop = __ballot_sync(0xFFFFFFFFu, eq < 8);
                         if (stop) { const int g = __ffs((int)stop) - 1; ml += 8 * g + __shfl_sync(0xFFFFFFFFu, eq, g); break; }
                         ml += 256;
                     }
                 }
-                // emit: literals [anchor, mpos) then the match
-                const uint32_t ll = (uint32_t)(mpos - anchor);
-                for (uint32_t i = lane; i < ll; i += 32) o_lit[nlit + i] = src[anchor + i];
-                if (lane == 0) { o_ll[nseq] = (uint16_t)ll; o_ml[nseq] = (uint16_t)(ml - 3); o_off[nseq] = off; }
-                nlit += ll; nseq++;
+                // emit: literals [anchor, mpos) are already / will be placed by the windows that hold them
+                if (lane == (int)(nseq & 31u)) { s_ll = mpos - anchor; s_ml = ml - 3; s_off = off; }
+                if ((nseq & 31u) == 31u) {
+                    const uint32_t at = nseq - 31u + (uint32_t)lane;
+                    o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off;
+                }
+                nseq++;
+                cov = cov || (p - mpos < ml);               // unsigned: mpos <= p < mpos + ml
                 anchor = mpos + ml; rep = off;
-                const size_t rel = anchor - wb;
-                // ceil(rel / stride) without an integer division (stride is 1..4)
-                next_lane = rel >= 32u * stride ? 32u
-                          : (stride == 1 ? (uint32_t)rel : (stride == 2 ? (uint32_t)((rel + 1) >> 1) : (stride == 4 ? (uint32_t)((rel + 3) >> 2) : (uint32_t)(((rel + 2) * 43691u) >> 17))));
+                next_lane = anchor - wb;                    // >= 32: the match runs past the window
             }
-            ip = anchor > wb + 32u * stride ? anchor : wb + 32u * stride;
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, !cov);
+            if (!cov) o_lit[nlit + __popc(lm & lt_mask)] = (uint8_t)cur;
+            nlit += (uint32_t)__popc(lm);
+            ip = anchor > wb + 32u ? anchor : wb + 32u;
         }
-        const uint32_t rest = (uint32_t)(hi - anchor);
-        for (uint32_t i = lane; i < rest; i += 32) o_lit[nlit + i] = src[anchor + i];
-        nlit += rest;
-    } else {
-        for (uint32_t i = lane; i < len; i += 32) o_lit[i] = src[lo + i];
-        nlit = len;
+        if (lane < (int)(nseq & 31u)) {
+            const uint32_t at = (nseq & ~31u) + (uint32_t)lane;
+            o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off;
+        }
     }
+    const uint32_t rest = hi32 - ip;
+    for (uint32_t i = lane; i < rest; i += 32) o_lit[nlit + i] = sb[ip + i];
+    nlit += rest;
     if (lane == 0) { a.blocks[b].nseq = nseq; a.blocks[b].nlit = nlit; }
 }
 
@@ -1016,7 +1048,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
     // the two entropy kernels are independent and both latency-bound: run them side by side, join in zk_block_finish_kernel
     if (!ws->side) {
-        ZKC_CUDA_OK(cudaStreamCreateWithFlags(&ws->side, cudaStreamNonBlocking));
+        ZKC_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
         ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming));
         ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming));
     }
