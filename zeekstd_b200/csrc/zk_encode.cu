@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         }
         uint32_t anchor = lo32;
         uint32_t rep = 0;                                   // last emitted offset (0 = none)
+        // repeat-offset history (A.5) as the decoder will hold it: blocks are coded independently, so repeat codes are used
+        // only once three explicit offsets have been coded in this block (the history is then certain); the first block of a
+        // frame starts from the known {1,4,8}.  o_off receives Offset_Values (1..3 = repeat codes, offset + 3 otherwise).
+        uint32_t r0 = 1, r1 = 4, r2 = 8, known = lo == fstart ? 3u : 0u;
         uint32_t misses = 0;                                // consecutive windows without a match: widen the stride (incompressible data)
         uint32_t s_ll = 0, s_ml = 0, s_off = 0;             // staged sequence (slot nseq & 31 lives in that lane)
         for (;;) {
@@ -190,7 +194,20 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
                     }
                 }
                 // emit: literals [anchor, mpos) are already / will be placed by the windows that hold them
-                if (lane == (int)(nseq & 31u)) { s_ll = mpos - anchor; s_ml = ml - 3; s_off = off; }
+                const uint32_t ll = mpos - anchor;
+                uint32_t ov = off + 3;
+                if (known == 3) {
+                    if (ll != 0) { if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3; }
+                    else { if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3; }
+                }
+                if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
+                else {
+                    const uint32_t idx = ov - 1 + (ll == 0);
+                    if (idx == 1) { const uint32_t t = r1; r1 = r0; r0 = t; }
+                    else if (idx == 2) { const uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
+                    else if (idx == 3) { const uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
+                }
+                if (lane == (int)(nseq & 31u)) { s_ll = ll; s_ml = ml - 3; s_off = ov; }
                 if ((nseq & 31u) == 31u) {
                     const uint32_t at = nseq - 31u + (uint32_t)lane;
                     o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off;
@@ -377,169 +394,216 @@ __device__ void zkc_fse_set_predefined(ZkcFse& t, int which) {
 }
 
 // =============================================================================================
-// K-C2s: sequence section -- one LANE per block.
-// Coding the sequences of a block is a serial chain (repeat-offset history, FSE state machine), so the parallel axis
-// is the block: every lane runs the same code over ITS block with ITS tables in shared memory.  The section is
-// written to a per-block scratch ([0,256) header + table descriptions, [256,..) bitstream) and moved into place by
-// the literal/assembly kernel.
+// K-C2s: sequence section -- one WARP per block.
+// The only serial part of coding a block's sequences is the FSE state chain (state -> bits out -> next state, A.6): four
+// integer operations and one shared-memory load per symbol.  Three lanes run the three chains (LL, OF, ML) over a tile of
+// 32 sequences; everything else is done by all 32 lanes, one sequence each: codes and histograms (pass A), the per-step
+// (deltaNbBits, deltaFindState) operands of the chains, extra bits, a warp scan of the bit counts and the packing of each
+// sequence's <= 87 bits into a shared-memory staging window that is flushed to HBM as whole words.  (The first version
+// ran one LANE per block with all of that on the serial chain: ~400 dependent instructions per sequence.)
+// The section is written to a per-block scratch ([0,256) header + table descriptions, [256,..) bitstream) and moved
+// into place by the assembly kernel.  Offsets arrive as Offset_Values (repeat codes resolved by K-C1).
 // =============================================================================================
-#define ZKC_SEQ_LPW 4              // chains per warp
-#define ZKC_SEQ_WARPS 4            // warps per CTA (same 16 tables per CTA; more warps hide the ALU latency of each chain)
-#define ZKC_SEQ_LANES (ZKC_SEQ_LPW * ZKC_SEQ_WARPS)
-struct ZkcSeqSlot { ZkcFse fse[3]; uint16_t cnt[3][64]; uint8_t symof[256]; };
+#define ZKC_SW 8                   // warps per CTA = blocks in flight per CTA
 struct ZkcTabs { uint32_t ll_base[36], ml_base[53]; uint8_t ll_bits[36], ml_bits[53], ll_code[64], ml_code[128]; };
 __device__ __forceinline__ uint32_t zkc_llc(const ZkcTabs& tb, uint32_t ll) { return ll < 64 ? tb.ll_code[ll] : (uint32_t)zk_highbit(ll) + 19; }
 __device__ __forceinline__ uint32_t zkc_mlc(const ZkcTabs& tb, uint32_t mlb) { return mlb < 128 ? tb.ml_code[mlb] : (uint32_t)zk_highbit(mlb) + 36; }
 
-// eight sequences in registers: the lanes of K-C2s stream through different blocks, so element-wise loads would stall the
-// warp on somebody's cache miss almost every iteration; 16-byte chunks are fetched one chunk ahead instead.
-struct ZkcSeq8 { uint4 ll, ml, o0, o1; };
-__device__ __forceinline__ void zkc_seq8_load(ZkcSeq8& r, const uint16_t* s_ll, const uint16_t* s_ml, const uint32_t* s_off, uint32_t chunk) {
-    r.ll = *(const uint4*)(s_ll + chunk * 8); r.ml = *(const uint4*)(s_ml + chunk * 8);
-    r.o0 = *(const uint4*)(s_off + chunk * 8); r.o1 = *(const uint4*)(s_off + chunk * 8 + 4);
-}
-__device__ __forceinline__ uint32_t zkc_u16_of(const uint4& v, int j) {
-    const uint32_t w = j < 2 ? v.x : (j < 4 ? v.y : (j < 6 ? v.z : v.w));
-    return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
-__device__ __forceinline__ uint32_t zkc_u32_of(const uint4& a, const uint4& b, int j) {
-    return j == 0 ? a.x : (j == 1 ? a.y : (j == 2 ? a.z : (j == 3 ? a.w : (j == 4 ? b.x : (j == 5 ? b.y : (j == 6 ? b.z : b.w))))));
-}
-__device__ __forceinline__ void zkc_u32_set(uint4& a, uint4& b, int j, uint32_t v) {
-    if (j == 0) a.x = v; else if (j == 1) a.y = v; else if (j == 2) a.z = v; else if (j == 3) a.w = v;
-    else if (j == 4) b.x = v; else if (j == 5) b.y = v; else if (j == 6) b.z = v; else b.w = v;
+struct ZkcSeqWarp {
+    ZkcFse fse[3];                                   // 0 LL, 1 OF, 2 ML
+    uint32_t cnt[3][64];
+    union {
+        uint8_t symof[3][256];                       // table build scratch (lanes 0..2 build one table each)
+        struct {
+            uint2 tin[3][33];                        // per step: (deltaNbBits, deltaFindState) of the step's symbol (padded: the three chains hit different banks)
+            uint16_t tout[3][34];                    // per step: (bits << 4) | nbBits written by the chain
+            uint32_t stage[96];                      // bit staging: [0] carries the partial word of the previous tile
+        } b;
+    } u;
+    uint8_t hdr[3][84];                              // table descriptions before they are concatenated
+};
+
+// one table (lane t of the warp): choose the mode, build the coding table, write its description.  -> false: not encodable
+__device__ bool zkc_seq_table(ZkcFse& ft, const uint32_t* cnt, int t, uint32_t nseq, uint8_t* symof, uint8_t* hdr, uint32_t* mode, uint32_t* nbytes) {
+    const int max_log = 8, nsym_all = t == 0 ? 36 : (t == 1 ? 32 : 53);
+    int last = nsym_all - 1; while (last > 0 && cnt[last] == 0) last--;
+    uint32_t distinct = 0; for (int q = 0; q <= last; q++) distinct += cnt[q] != 0;
+    if (distinct == 1) {
+        ft.mode = 1; ft.rle_sym = (uint8_t)last; ft.log = 0;
+        ft.state_tbl[0] = 0; ft.delta_nb[last] = 0; ft.delta_find[last] = 0;             // the chain then idles at state 0, emitting no bits
+        hdr[0] = (uint8_t)last; *mode = 1; *nbytes = 1;
+        return true;
+    }
+    if (nseq < 48 && (t != 1 || last <= 28)) { zkc_fse_set_predefined(ft, t); zkc_fse_build(ft, symof); *mode = 0; *nbytes = 0; return true; }
+    int lg = zk_highbit(nseq) - 1; if (lg < 5) lg = 5; if (lg > max_log) lg = max_log;
+    int need = zk_highbit(distinct) + 1; if (lg < need) lg = need; if (lg > max_log) return false;
+    zkc_fse_normalize(ft, cnt, last + 1, nseq, lg);
+    ft.mode = 2;
+    zkc_fse_build(ft, symof);
+    const uint32_t hb = zkc_fse_write_ncount(ft, hdr, 84);
+    if (!hb) return false;
+    *mode = 2; *nbytes = hb;
+    return true;
 }
 
-// returns false if the section cannot be encoded within the scratch (the block then becomes a Raw block)
-__device__ bool zkc_encode_sequences(ZkcSeqSlot& sl, const ZkcTabs& tb, const uint16_t* s_ll, const uint16_t* s_ml, uint32_t* s_off, uint32_t nseq,
-                                     bool first_block, uint8_t* out, uint32_t* hdr_bytes, uint32_t* bits_bytes) {
-    const uint32_t nchunks = (nseq + 7) / 8;
-    // ---- pass A (forward): repeat-offset substitution (serial history, A.5) turns s_off into Offset_Value in place, and the
-    // three code histograms are counted.  Blocks are coded independently, so repeat codes are used only once three explicit
-    // offsets have been coded in this block (the decoder's history is then certain); the first block of a frame starts from
-    // the known {1,4,8}.
-    for (int i = 0; i < 3 * 64; i++) (&sl.cnt[0][0])[i] = 0;          // (u16 counters: a block has at most 8192 sequences)
-    {
-        uint32_t r0 = 1, r1 = 4, r2 = 8, known = first_block ? 3 : 0;
-        ZkcSeq8 cur, nxt;
-        zkc_seq8_load(cur, s_ll, s_ml, s_off, 0);
-        for (uint32_t c = 0; c < nchunks; c++) {
-            if (c + 1 < nchunks) zkc_seq8_load(nxt, s_ll, s_ml, s_off, c + 1);
-            if ((c & 3) == 0 && c + 24 < nchunks) {     // pull the cache lines ~24 chunks ahead towards L1 (DRAM latency >> one chunk of work)
-                zk_prefetch_l1(s_off + (c + 24) * 8);
-                if ((c & 7) == 0) { zk_prefetch_l1(s_ll + (c + 24) * 8); zk_prefetch_l1(s_ml + (c + 24) * 8); }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (c * 8 + j < nseq) {
-                    const uint32_t off = zkc_u32_of(cur.o0, cur.o1, j), ll = zkc_u16_of(cur.ll, j), mlb = zkc_u16_of(cur.ml, j);
-                    uint32_t ov = off + 3;
-                    if (known == 3) {
-                        if (ll != 0) { if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3; }
-                        else { if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3; }
-                    }
-                    if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
-                    else {
-                        uint32_t idx = ov - 1 + (ll == 0);
-                        if (idx == 1) { uint32_t t = r1; r1 = r0; r0 = t; }
-                        else if (idx == 2) { uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
-                        else if (idx == 3) { uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
-                    }
-                    zkc_u32_set(cur.o0, cur.o1, j, ov);
-                    sl.cnt[0][zkc_llc(tb, ll)]++; sl.cnt[1][zk_highbit(ov)]++; sl.cnt[2][zkc_mlc(tb, mlb)]++;
-                }
-            }
-            *(uint4*)(s_off + c * 8) = cur.o0; *(uint4*)(s_off + c * 8 + 4) = cur.o1;
-            cur = nxt;
-        }
+// whole warp; returns false if the section cannot be encoded within the scratch (the block then becomes a Raw block)
+__device__ bool zkc_encode_sequences(ZkcSeqWarp& sw, const ZkcTabs& tb, const uint16_t* s_ll, const uint16_t* s_ml, const uint32_t* s_ov, uint32_t nseq,
+                                     uint8_t* out, uint32_t* hdr_bytes, uint32_t* bits_bytes, int lane) {
+    // ---- pass A: code histograms, one sequence per lane
+    for (int i = lane; i < 3 * 64; i += 32) (&sw.cnt[0][0])[i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < nseq; i += 32) {
+        atomicAdd(&sw.cnt[0][zkc_llc(tb, s_ll[i])], 1u); atomicAdd(&sw.cnt[1][zk_highbit(s_ov[i])], 1u); atomicAdd(&sw.cnt[2][zkc_mlc(tb, s_ml[i])], 1u);
     }
+    __syncwarp();
+    // ---- tables: lanes 0..2 build one each
+    uint32_t mode = 0, nb_t = 0; bool ok = true;
+    if (lane < 3) ok = zkc_seq_table(sw.fse[lane], sw.cnt[lane], lane, nseq, sw.u.symof[lane], sw.hdr[lane], &mode, &nb_t);
+    if (!__all_sync(0xFFFFFFFFu, ok)) return false;
     uint32_t hp = 0;
-    if (nseq < 128) out[hp++] = (uint8_t)nseq;
-    else if (nseq < 0x7F00) { out[hp++] = (uint8_t)((nseq >> 8) + 128); out[hp++] = (uint8_t)nseq; }
-    else { out[hp++] = 255; out[hp++] = (uint8_t)(nseq - 0x7F00); out[hp++] = (uint8_t)((nseq - 0x7F00) >> 8); }
-    const uint32_t modes_at = hp++;
-    uint32_t modes = 0;
-    for (int t = 0; t < 3; t++) {
-        ZkcFse& ft = sl.fse[t];
-        const int max_log = 8, nsym_all = t == 0 ? 36 : (t == 1 ? 32 : 53);
-        int last = nsym_all - 1; while (last > 0 && sl.cnt[t][last] == 0) last--;
-        uint32_t distinct = 0; for (int q = 0; q <= last; q++) distinct += sl.cnt[t][q] != 0;
-        if (distinct == 1) { ft.mode = 1; ft.rle_sym = (uint8_t)last; ft.log = 0; out[hp++] = (uint8_t)last; modes |= 1u << (6 - 2 * t); }
-        else if (nseq < 48 && (t != 1 || last <= 28)) { zkc_fse_set_predefined(ft, t); zkc_fse_build(ft, sl.symof); }
-        else {
-            int lg = zk_highbit(nseq) - 1; if (lg < 5) lg = 5; if (lg > max_log) lg = max_log;
-            int need = zk_highbit(distinct) + 1; if (lg < need) lg = need; if (lg > max_log) return false;
-            zkc_fse_normalize(ft, sl.cnt[t], last + 1, nseq, lg);
-            ft.mode = 2;
-            zkc_fse_build(ft, sl.symof);
-            uint32_t hb = zkc_fse_write_ncount(ft, out + hp, ZKC_SEQHDR - 6 - hp);
-            if (!hb) return false;
-            hp += hb; modes |= 2u << (6 - 2 * t);
-        }
+    if (lane == 0) {
+        if (nseq < 128) out[hp++] = (uint8_t)nseq;
+        else if (nseq < 0x7F00) { out[hp++] = (uint8_t)((nseq >> 8) + 128); out[hp++] = (uint8_t)nseq; }
+        else { out[hp++] = 255; out[hp++] = (uint8_t)(nseq - 0x7F00); out[hp++] = (uint8_t)((nseq - 0x7F00) >> 8); }
     }
-    out[modes_at] = (uint8_t)modes;
-    // ---- pass B (backward): the bitstream, last sequence first (mirror of the decoder's order, A.5)
-    ZkcBitWW w; w.init(out + ZKC_SEQHDR, ZKC_SEQSEC - ZKC_SEQHDR);
-    uint32_t st_ll = 0, st_of = 0, st_ml = 0;
-    bool first = true;
+    hp = __shfl_sync(0xFFFFFFFFu, hp, 0);
     {
-        ZkcSeq8 cur, nxt;
-        zkc_seq8_load(cur, s_ll, s_ml, s_off, nchunks - 1);
-        for (uint32_t c = nchunks; c-- > 0;) {
-            if (c > 0) zkc_seq8_load(nxt, s_ll, s_ml, s_off, c - 1);
-            if ((c & 3) == 0 && c >= 24) {
-                zk_prefetch_l1(s_off + (c - 24) * 8);
-                if ((c & 7) == 0) { zk_prefetch_l1(s_ll + (c - 24) * 8); zk_prefetch_l1(s_ml + (c - 24) * 8); }
-            }
-#pragma unroll
-            for (int j = 7; j >= 0; j--) {
-                if (c * 8 + j < nseq) {
-                    const uint32_t llv = zkc_u16_of(cur.ll, j), mlb = zkc_u16_of(cur.ml, j), ov = zkc_u32_of(cur.o0, cur.o1, j);
-                    const uint32_t llc = zkc_llc(tb, llv), mlc = zkc_mlc(tb, mlb), ofc = (uint32_t)zk_highbit(ov);
-                    if (first) {
-                        zkc_fse_init_state(sl.fse[2], mlc, st_ml); zkc_fse_init_state(sl.fse[1], ofc, st_of); zkc_fse_init_state(sl.fse[0], llc, st_ll);
-                        first = false;
-                    } else {
-                        zkc_fse_encode(sl.fse[1], w, ofc, st_of);
-                        zkc_fse_encode(sl.fse[2], w, mlc, st_ml);
-                        zkc_fse_encode(sl.fse[0], w, llc, st_ll);
-                    }
-                    w.add(llv - tb.ll_base[llc], tb.ll_bits[llc]);
-                    w.add(mlb + 3 - tb.ml_base[mlc], tb.ml_bits[mlc]);
-                    w.add(ov - (1u << ofc), (int)ofc);
-                }
-            }
-            cur = nxt;
-        }
+        const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, mode, 0), m1 = __shfl_sync(0xFFFFFFFFu, mode, 1), m2 = __shfl_sync(0xFFFFFFFFu, mode, 2);
+        const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, nb_t, 0), n1 = __shfl_sync(0xFFFFFFFFu, nb_t, 1), n2 = __shfl_sync(0xFFFFFFFFu, nb_t, 2);
+        if (lane == 0) out[hp] = (uint8_t)((m0 << 6) | (m1 << 4) | (m2 << 2));
+        hp++;
+        if (hp + n0 + n1 + n2 > ZKC_SEQHDR - 6) return false;
+        for (uint32_t i = lane; i < n0; i += 32) out[hp + i] = sw.hdr[0][i];
+        for (uint32_t i = lane; i < n1; i += 32) out[hp + n0 + i] = sw.hdr[1][i];
+        for (uint32_t i = lane; i < n2; i += 32) out[hp + n0 + n1 + i] = sw.hdr[2][i];
+        hp += n0 + n1 + n2;
     }
-    zkc_fse_flush(sl.fse[2], w, st_ml); zkc_fse_flush(sl.fse[1], w, st_of); zkc_fse_flush(sl.fse[0], w, st_ll);
-    const uint32_t sb = w.finish();
-    if (!sb) return false;
+    __syncwarp();                                    // the build scratch (union) is dead from here on
+    // ---- pass B (backward): the bitstream, last sequence first (mirror of the decoder's order, A.5)
+    uint32_t* const gw = (uint32_t*)(out + ZKC_SEQHDR);
+    const uint32_t cap_words = (ZKC_SEQSEC - ZKC_SEQHDR) / 4;
+    for (int i = lane; i < 96; i += 32) sw.u.b.stage[i] = 0;
+    uint32_t st = 0;                                 // lanes 0..2: state of chain `lane`
+    uint32_t bitpos = 0;                             // bits emitted so far
+    bool first = true, ovf = false;
+    const uint32_t lt_mask = (1u << lane) - 1u; (void)lt_mask;
+    for (uint32_t hi_i = nseq; hi_i > 0;) {
+        const uint32_t cntT = hi_i < 32u ? hi_i : 32u;
+        const bool act = (uint32_t)lane < cntT;
+        const uint32_t idx = act ? hi_i - 1u - (uint32_t)lane : 0u;       // step `lane` of this tile codes sequence idx
+        const uint32_t llv = s_ll[idx], mlb = s_ml[idx], ov = s_ov[idx];
+        const uint32_t llc = zkc_llc(tb, llv), mlc = zkc_mlc(tb, mlb), ofc = (uint32_t)zk_highbit(ov);
+        if (act) {
+            sw.u.b.tin[0][lane] = make_uint2(sw.fse[0].delta_nb[llc], (uint32_t)(int)sw.fse[0].delta_find[llc]);
+            sw.u.b.tin[1][lane] = make_uint2(sw.fse[1].delta_nb[ofc], (uint32_t)(int)sw.fse[1].delta_find[ofc]);
+            sw.u.b.tin[2][lane] = make_uint2(sw.fse[2].delta_nb[mlc], (uint32_t)(int)sw.fse[2].delta_find[mlc]);
+        }
+        __syncwarp();
+        if (lane < 3) {                              // the three chains
+            const uint16_t* stt = sw.fse[lane].state_tbl;
+            const uint2* ti = sw.u.b.tin[lane]; uint16_t* to = sw.u.b.tout[lane];
+            uint32_t j = 0;
+            if (first) {
+                if (sw.fse[lane].mode == 1) st = 0;
+                else {
+                    const uint2 d = ti[0];
+                    const uint32_t nb_out = (d.x + (1u << 15)) >> 16, value = (nb_out << 16) - d.x;
+                    st = stt[(value >> nb_out) + (int)d.y];
+                }
+                to[0] = 0; j = 1;
+            }
+#pragma unroll 4
+            for (; j < cntT; j++) {
+                const uint2 d = ti[j];
+                const uint32_t nb_out = (st + d.x) >> 16;
+                to[j] = (uint16_t)(((st & ((1u << nb_out) - 1u)) << 4) | nb_out);
+                st = stt[(st >> nb_out) + (int)d.y];
+            }
+        }
+        first = false;
+        __syncwarp();
+        // this lane's sequence: state bits (OF, ML, LL), then extra bits (LL, ML, OF)
+        unsigned long long v = 0; uint32_t n1 = 0, v2 = 0, n2 = 0;
+        if (act) {
+            const uint32_t o = sw.u.b.tout[1][lane], m = sw.u.b.tout[2][lane], l = sw.u.b.tout[0][lane];
+            v = o >> 4; n1 = o & 15u;
+            v |= (unsigned long long)(m >> 4) << n1; n1 += m & 15u;
+            v |= (unsigned long long)(l >> 4) << n1; n1 += l & 15u;
+            v |= (unsigned long long)(llv - tb.ll_base[llc]) << n1; n1 += tb.ll_bits[llc];
+            v |= (unsigned long long)(mlb + 3u - tb.ml_base[mlc]) << n1; n1 += tb.ml_bits[mlc];
+            v2 = ov - (1u << ofc); n2 = ofc;
+        }
+        uint32_t incl = n1 + n2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t base_bit = bitpos & 31u;
+        if (act) {
+            uint32_t pos = base_bit + incl - (n1 + n2);
+            if (n1) {
+                const uint32_t w = pos >> 5, sh = pos & 31u;
+                const unsigned long long lo = v << sh;
+                atomicOr(&sw.u.b.stage[w], (uint32_t)lo);
+                if (lo >> 32) atomicOr(&sw.u.b.stage[w + 1], (uint32_t)(lo >> 32));
+                if (sh) { const uint32_t hi = (uint32_t)(v >> (64u - sh)); if (hi) atomicOr(&sw.u.b.stage[w + 2], hi); }
+            }
+            pos += n1;
+            if (n2) {
+                const uint32_t w = pos >> 5, sh = pos & 31u;
+                const unsigned long long lo = (unsigned long long)v2 << sh;
+                atomicOr(&sw.u.b.stage[w], (uint32_t)lo);
+                if (lo >> 32) atomicOr(&sw.u.b.stage[w + 1], (uint32_t)(lo >> 32));
+            }
+        }
+        __syncwarp();
+        // flush the full words, keep the partial one as word 0 of the next tile
+        const uint32_t nwords = (base_bit + tile_bits) >> 5, word0 = bitpos >> 5;
+        if (word0 + nwords > cap_words) ovf = true;
+        else for (uint32_t w = lane; w < nwords; w += 32) gw[word0 + w] = sw.u.b.stage[w];
+        const uint32_t carry = sw.u.b.stage[nwords];
+        __syncwarp();
+        for (uint32_t w = lane; w <= nwords + 2; w += 32) sw.u.b.stage[w] = w == 0 ? carry : 0u;
+        __syncwarp();
+        bitpos += tile_bits;
+        hi_i -= cntT;
+    }
+    // final states (ML, OF, LL), then the end mark
+    const uint32_t s_l = __shfl_sync(0xFFFFFFFFu, st, 0), s_o = __shfl_sync(0xFFFFFFFFu, st, 1), s_m = __shfl_sync(0xFFFFFFFFu, st, 2);
+    const uint32_t lg_l = (uint32_t)sw.fse[0].log, lg_o = (uint32_t)sw.fse[1].log, lg_m = (uint32_t)sw.fse[2].log;
+    unsigned long long fin = s_m & ((1u << lg_m) - 1u); uint32_t nf = lg_m;
+    fin |= (unsigned long long)(s_o & ((1u << lg_o) - 1u)) << nf; nf += lg_o;
+    fin |= (unsigned long long)(s_l & ((1u << lg_l) - 1u)) << nf; nf += lg_l;
+    fin |= 1ull << nf; nf += 1;
+    const uint32_t base_bit = bitpos & 31u, word0 = bitpos >> 5;
+    const unsigned long long tail = ((unsigned long long)sw.u.b.stage[0]) | (fin << base_bit);      // <= 31 + 25 bits
+    const uint32_t total_bits = bitpos + nf;
+    const uint32_t sb = (total_bits + 7u) >> 3;
+    if (ovf || word0 + 2 > cap_words) return false;
+    if (lane == 0) { gw[word0] = (uint32_t)tail; gw[word0 + 1] = (uint32_t)(tail >> 32); }
     *hdr_bytes = hp; *bits_bytes = sb;
     return true;
 }
 
-__global__ void __launch_bounds__(32 * ZKC_SEQ_WARPS) zk_seq_enc_kernel(ZkEncodeArgs a) {
+__global__ void __launch_bounds__(32 * ZKC_SW) zk_seq_enc_kernel(ZkEncodeArgs a) {
     ZK_DYN_SMEM(smem);
     ZkcTabs* tb = (ZkcTabs*)smem;
-    ZkcSeqSlot* slots = (ZkcSeqSlot*)(smem + ((sizeof(ZkcTabs) + 15) & ~(size_t)15));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, nt = 32 * ZKC_SEQ_WARPS;
+    ZkcSeqWarp* sws = (ZkcSeqWarp*)(smem + ((sizeof(ZkcTabs) + 15) & ~(size_t)15));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, nt = 32 * ZKC_SW;
     for (int i = tid; i < 36; i += nt) { tb->ll_base[i] = ZK_LL_BASE[i]; tb->ll_bits[i] = ZK_LL_BITS[i]; }
     for (int i = tid; i < 53; i += nt) { tb->ml_base[i] = ZK_ML_BASE[i]; tb->ml_bits[i] = ZK_ML_BITS[i]; }
     for (int i = tid; i < 64; i += nt) tb->ll_code[i] = ZKC_LL_CODE[i];
     for (int i = tid; i < 128; i += nt) tb->ml_code[i] = ZKC_ML_CODE[i];
     __syncthreads();
-    const uint32_t b = (blockIdx.x * ZKC_SEQ_WARPS + warp) * ZKC_SEQ_LPW + lane;
-    if (lane < ZKC_SEQ_LPW && b < a.n_blocks) {
-        const uint32_t nseq = a.blocks[b].nseq;
-        uint32_t hb = 0, sb = 0;
-        if (nseq) {
-            const bool ok = zkc_encode_sequences(slots[warp * ZKC_SEQ_LPW + lane], *tb, a.seq_ll + (size_t)b * ZKC_MAXSEQ, a.seq_ml + (size_t)b * ZKC_MAXSEQ,
-                                                 a.seq_off + (size_t)b * ZKC_MAXSEQ, nseq, b % a.blocks_per_frame == 0, a.seqsec + (size_t)b * ZKC_SEQSEC, &hb, &sb);
-            if (!ok) { hb = 0; sb = 0; }
-        }
-        a.blocks[b].seq_hdr = hb; a.blocks[b].seq_bits = sb;
+    const uint32_t b = blockIdx.x * ZKC_SW + warp;
+    if (b >= a.n_blocks) return;
+    const uint32_t nseq = a.blocks[b].nseq;
+    uint32_t hb = 0, sb = 0;
+    if (nseq) {
+        const bool ok = zkc_encode_sequences(sws[warp], *tb, a.seq_ll + (size_t)b * ZKC_MAXSEQ, a.seq_ml + (size_t)b * ZKC_MAXSEQ,
+                                             a.seq_off + (size_t)b * ZKC_MAXSEQ, nseq, a.seqsec + (size_t)b * ZKC_SEQSEC, &hb, &sb, lane);
+        if (!ok) { hb = 0; sb = 0; }
     }
+    if (lane == 0) { a.blocks[b].seq_hdr = hb; a.blocks[b].seq_bits = sb; }
 }
 
 #define ZKC_BITBUF 12288u               // shared-memory bit buffer: one Huffman stream (<= 8192 symbols x 11 bits) or the sequence bitstream
@@ -1044,7 +1108,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ws->prof.begin(5, stream);
     ZK_LAUNCH(zk_match_kernel, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
     ws->prof.end(5, stream);
-    const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqSlot) * ZKC_SEQ_LANES;
+    const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqWarp) * ZKC_SW;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
     // the two entropy kernels are independent and both latency-bound: run them side by side, join in zk_block_finish_kernel
     if (!ws->side) {
@@ -1055,7 +1119,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ws->prof.begin(6, stream);
     ZKC_CUDA_OK(cudaEventRecord(ws->ev_a, stream));
     ZKC_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_a, 0));
-    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SEQ_LANES - 1) / ZKC_SEQ_LANES), 32 * ZKC_SEQ_WARPS, seq_smem, ws->side, a);
+    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SW - 1) / ZKC_SW), 32 * ZKC_SW, seq_smem, ws->side, a);
     ZKC_CUDA_OK(cudaEventRecord(ws->ev_b, ws->side));
     ZK_LAUNCH(zk_lit_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
     ZKC_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_b, 0));
