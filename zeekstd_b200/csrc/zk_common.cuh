@@ -212,16 +212,8 @@ struct ZkFwdBits {
 };
 
 // -------------------------------------------------------------------------------------------
-// FSE decoding tables (A.6).  Sequence tables use the "fat" cell libzstd also uses so that one
-// shared-memory load yields everything a symbol needs.
+// FSE tables (A.6): symbol code -> value baseline / extra bits
 // -------------------------------------------------------------------------------------------
-struct __align__(8) ZkSeqCell {
-    uint32_t base_value;     // LL/ML: length baseline; OF: 1 << code
-    uint16_t next_base;      // next-state baseline
-    uint8_t add_bits;        // extra bits to read for the value
-    uint8_t nb_bits;         // bits to read for the next state
-};
-
 __constant__ uint32_t ZK_LL_BASE[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536};
 __constant__ uint8_t ZK_LL_BITS[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16};
 __constant__ uint32_t ZK_ML_BASE[53] = {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539};

@@ -220,16 +220,26 @@ __global__ void __launch_bounds__(128) zk_scan_kernel(ZkDecodeArgs a) {
 // in shared memory, so one issued instruction advances up to ZK_SEQ_LANES chains.
 // =============================================================================================
 #define ZK_SEQ_LPW 3              // chains per warp
-#define ZK_SEQ_WARPS 3            // warps per CTA: the same 9 x 11.7 KiB of tables per CTA (2 CTAs / SM) spread over more warps --
+#define ZK_SEQ_WARPS 3            // warps per CTA: 9 x 5.6 KiB of tables per CTA (4 CTAs / SM) spread over more warps --
 #define ZK_SEQ_LANES (ZK_SEQ_LPW * ZK_SEQ_WARPS)   // each chain is ALU-latency bound, so more warps per SM hide more of it
 
+// Thin decoding cell: one 32-bit shared-memory load yields everything on the dependency chain of a sequence (bits to
+// skip, bits of the next state, next-state baseline); the value baselines come from small per-CTA tables by symbol code,
+// off the chain.  (The first version used libzstd's 8-byte cell: 11.7 KiB of tables per chain, 18 chains per SM.)
+//   [0,9) next-state baseline   [9,13) nbBits   [13,18) extra bits   [18,24) symbol code
+#define ZK_CELL(code, add, nb, base) ((uint32_t)(base) | ((uint32_t)(nb) << 9) | ((uint32_t)(add) << 13) | ((uint32_t)(code) << 18))
+#define ZK_CELL_BASE(c) ((c) & 511u)
+#define ZK_CELL_NB(c) (((c) >> 9) & 15u)
+#define ZK_CELL_ADD(c) (((c) >> 13) & 31u)
+#define ZK_CELL_CODE(c) (((c) >> 18) & 63u)
+
 struct ZkSeqSlot {
-    ZkSeqCell ll[512], ml[512], of[256];       // 10 KiB
+    uint32_t ll[512], ml[512], of[256];        // 5 KiB
     int16_t cnt[3][64];
     uint16_t nxt[64];
-    uint8_t symof[512];
     int tbl_log[3], tbl_nsym[3], tbl_mode[3];  // mode: 0 = counts in cnt[t], 1 = RLE (cnt[t][0] = symbol)
 };
+struct ZkSeqTabs { uint32_t ll_base[36], ml_base[53]; };
 
 // Locate the three table descriptions of a block (A.5) and parse those that are wanted into sl.cnt[t]
 // (t: 0 LL, 1 OF, 2 ML).  Returns 0 or a zstd code.  *bits_off = start of the sequence bitstream.
@@ -261,8 +271,8 @@ __device__ int zk_locate_seq_tables(ZkSeqSlot& sl, const uint8_t* b, uint32_t bs
             pos += 1;
         } else if (m == 2) {
             int ns, lg;
-            // an unwanted table is parsed into the (not yet used) nxt/symof scratch just to learn its length
-            uint32_t used = zk_fse_read_ncount(b + pos, bsize - pos, max_log, max_sym, want ? sl.cnt[t] : (int16_t*)sl.symof, &ns, &lg);
+            // an unwanted table is parsed into the (not yet used) nxt scratch just to learn its length
+            uint32_t used = zk_fse_read_ncount(b + pos, bsize - pos, max_log, max_sym, want ? sl.cnt[t] : (int16_t*)sl.nxt, &ns, &lg);
             if (!used) return ZKZ_CORRUPTION;
             if (want) { sl.tbl_mode[t] = 0; sl.tbl_nsym[t] = ns; sl.tbl_log[t] = lg; }
             pos += used;
@@ -275,47 +285,41 @@ __device__ int zk_locate_seq_tables(ZkSeqSlot& sl, const uint8_t* b, uint32_t bs
     return 0;
 }
 
-// Build one sequence decoding table from sl.cnt[t] (A.6).
+// Build one sequence decoding table from sl.cnt[t] (A.6).  The symbol spread is written into the cell array itself and
+// converted to cells in place.
 __device__ int zk_build_seq_table(ZkSeqSlot& sl, int t) {
-    ZkSeqCell* cell = t == 0 ? sl.ll : (t == 1 ? sl.of : sl.ml);
+    uint32_t* cell = t == 0 ? sl.ll : (t == 1 ? sl.of : sl.ml);
     if (sl.tbl_mode[t] == 1) {
-        int s = sl.cnt[t][0];
-        ZkSeqCell c; c.next_base = 0; c.nb_bits = 0;
-        if (t == 0) { c.base_value = ZK_LL_BASE[s]; c.add_bits = ZK_LL_BITS[s]; }
-        else if (t == 1) { c.base_value = 1u << s; c.add_bits = (uint8_t)s; }
-        else { c.base_value = ZK_ML_BASE[s]; c.add_bits = ZK_ML_BITS[s]; }
-        cell[0] = c;
+        const uint32_t sy = (uint32_t)sl.cnt[t][0];
+        const uint32_t add = t == 0 ? ZK_LL_BITS[sy] : (t == 1 ? sy : ZK_ML_BITS[sy]);
+        cell[0] = ZK_CELL(sy, add, 0, 0);
         return 0;
     }
     int log = sl.tbl_log[t], S = 1 << log, nsym = sl.tbl_nsym[t], high = S - 1;
-    uint8_t* symof = sl.symof; uint16_t* nxt = sl.nxt; const int16_t* cnt = sl.cnt[t];
+    uint16_t* nxt = sl.nxt; const int16_t* cnt = sl.cnt[t];
     for (int s = 0; s < nsym; s++) {
-        if (cnt[s] == -1) { symof[high--] = (uint8_t)s; nxt[s] = 1; }
+        if (cnt[s] == -1) { cell[high--] = (uint32_t)s; nxt[s] = 1; }
         else nxt[s] = (uint16_t)cnt[s];
     }
     int step = (S >> 1) + (S >> 3) + 3, pos = 0;
     for (int s = 0; s < nsym; s++)
         for (int q = 0; q < cnt[s]; q++) {
-            symof[pos] = (uint8_t)s;
+            cell[pos] = (uint32_t)s;
             do { pos = (pos + step) & (S - 1); } while (pos > high);
         }
     if (pos != 0) return ZKZ_CORRUPTION;
     for (int u = 0; u < S; u++) {
-        int s = symof[u];
-        uint32_t x = nxt[s]++;
-        int nb = log - zk_highbit(x);
-        ZkSeqCell c;
-        c.nb_bits = (uint8_t)nb; c.next_base = (uint16_t)((x << nb) - S);
-        if (t == 0) { c.base_value = ZK_LL_BASE[s]; c.add_bits = ZK_LL_BITS[s]; }
-        else if (t == 1) { c.base_value = 1u << s; c.add_bits = (uint8_t)s; }
-        else { c.base_value = ZK_ML_BASE[s]; c.add_bits = ZK_ML_BITS[s]; }
-        cell[u] = c;
+        const uint32_t sy = cell[u];
+        const uint32_t x = nxt[sy]++;
+        const int nb = log - zk_highbit(x);
+        const uint32_t add = t == 0 ? ZK_LL_BITS[sy] : (t == 1 ? sy : ZK_ML_BITS[sy]);
+        cell[u] = ZK_CELL(sy, add, nb, (x << nb) - (uint32_t)S);
     }
     return 0;
 }
 
 // Decode all sequences of one block (lane-local).  Returns 0 or a zstd code.
-__device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkDecodeArgs& a, const ZkBlock& blk, uint32_t bidx, const uint8_t* ebase) {
+__device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkSeqTabs& tb, const ZkDecodeArgs& a, const ZkBlock& blk, uint32_t bidx, const uint8_t* ebase) {
     const uint8_t* b = ebase + blk.src;
     uint32_t bits_off = 0;
     int st = zk_locate_seq_tables(sl, b, blk.size, blk.ll_ref < 0, blk.of_ref < 0, blk.ml_ref < 0, &bits_off);
@@ -337,17 +341,18 @@ __device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkDecodeArgs& a, c
     uint32_t* o_off = a.seq_off + blk.seq_base;
     const uint32_t nseq = blk.nseq;
     for (uint32_t i = 0; i < nseq; i++) {
-        ZkSeqCell cl = sl.ll[s_l], co = sl.of[s_o], cm = sl.ml[s_m];
+        const uint32_t cl = sl.ll[s_l], co = sl.of[s_o], cm = sl.ml[s_m];
         br.refill();                                                  // <= 31 bits follow
-        uint32_t ofv = co.base_value + br.read(co.add_bits);
+        const uint32_t ofc = ZK_CELL_CODE(co);
+        uint32_t ofv = (1u << ofc) + br.read((int)ofc);
         br.refill();                                                  // <= 16 + 16 bits follow
-        uint32_t mlv = cm.base_value + br.read(cm.add_bits);
-        uint32_t llv = cl.base_value + br.read(cl.add_bits);
+        uint32_t mlv = tb.ml_base[ZK_CELL_CODE(cm)] + br.read((int)ZK_CELL_ADD(cm));
+        uint32_t llv = tb.ll_base[ZK_CELL_CODE(cl)] + br.read((int)ZK_CELL_ADD(cl));
         br.refill();                                                  // <= 9 + 9 + 8 bits follow
         if (i + 1 < nseq) {
-            s_l = cl.next_base + br.read(cl.nb_bits);
-            s_m = cm.next_base + br.read(cm.nb_bits);
-            s_o = co.next_base + br.read(co.nb_bits);
+            s_l = ZK_CELL_BASE(cl) + br.read((int)ZK_CELL_NB(cl));
+            s_m = ZK_CELL_BASE(cm) + br.read((int)ZK_CELL_NB(cm));
+            s_o = ZK_CELL_BASE(co) + br.read((int)ZK_CELL_NB(co));
         }
         // repeat-offset history, kept symbolic w.r.t. the (unknown) state entering this block
         uint32_t off;
@@ -377,8 +382,12 @@ __device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkDecodeArgs& a, c
 
 __global__ void __launch_bounds__(32 * ZK_SEQ_WARPS) zk_seq_kernel(ZkDecodeArgs a) {
     ZK_DYN_SMEM(smem);
-    ZkSeqSlot* slots = (ZkSeqSlot*)smem;
+    ZkSeqTabs* tb = (ZkSeqTabs*)smem;
+    ZkSeqSlot* slots = (ZkSeqSlot*)(smem + ((sizeof(ZkSeqTabs) + 15) & ~(size_t)15));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 36; i += 32 * ZK_SEQ_WARPS) tb->ll_base[i] = ZK_LL_BASE[i];
+    for (int i = threadIdx.x; i < 53; i += 32 * ZK_SEQ_WARPS) tb->ml_base[i] = ZK_ML_BASE[i];
+    __syncthreads();
     if (a.counters->overflow) return;
     const uint32_t n = a.counters->n_seq_blocks;
     for (;;) {                                  // every warp pulls its own groups of ZK_SEQ_LPW blocks
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(32 * ZK_SEQ_WARPS) zk_seq_kernel(ZkDecodeArgs 
             uint32_t bidx = a.seq_list[my];
             ZkBlock blk = a.blocks[bidx];
             if (a.entries[blk.entry].status == 0) {
-                int st = zk_decode_block_sequences(slots[warp * ZK_SEQ_LPW + lane], a, blk, bidx, a.comp + a.c_off[blk.entry]);
+                int st = zk_decode_block_sequences(slots[warp * ZK_SEQ_LPW + lane], *tb, a, blk, bidx, a.comp + a.c_off[blk.entry]);
                 a.blocks[bidx].status = st ? -st : 0;
             }
         }
@@ -630,7 +639,7 @@ __device__ __forceinline__ void zk_d2_abort(ZkD2Smem& sm, int code) { atomicCAS(
 __device__ __forceinline__ bool zk_d2_aborted(ZkD2Smem& sm) { return __any_sync(0xFFFFFFFFu, *(volatile int*)&sm.abort_code != 0); }
 
 // advance the in-order prefixes as far as the per-chunk flags allow (any thread may do this at any time)
-__device__ __forceinline__ void zk_d2_help(ZkD2Smem& sm) {
+__device__ __noinline__ void zk_d2_help(ZkD2Smem& sm) {
     uint32_t dc = ZK_VOL(sm.done_chunk), dc0 = dc, dp = 0;
     while (ZK_VOL(sm.done[dc & (ZK_D2_META - 1)]) == dc + 1) { dp = ZK_VOL(sm.end[dc & (ZK_D2_META - 1)]); dc++; }
     if (dc != dc0) { atomicMax(&sm.done_pos, dp); __threadfence_block(); atomicMax(&sm.done_chunk, dc); }
@@ -656,7 +665,7 @@ __device__ __forceinline__ bool zk_d2_ext_ready(ZkD2Smem& sm, uint32_t c, uint32
 }
 
 // warp-cooperative copy of n bytes HBM -> HBM, non-overlapping (or src entirely before dst with distance >= n)
-__device__ __forceinline__ void zk_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+__device__ __noinline__ void zk_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
     uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
     if (lane < (int)head) dst[lane] = src[lane];
@@ -686,7 +695,7 @@ __device__ __forceinline__ void zk_warp_copy(uint8_t* dst, const uint8_t* src, u
     for (uint32_t i = done + lane; i < n; i += 32) dst[i] = src[i];
 }
 
-__device__ __forceinline__ void zk_warp_fill(uint8_t* dst, uint32_t byte, uint32_t n, int lane) {
+__device__ __noinline__ void zk_warp_fill(uint8_t* dst, uint32_t byte, uint32_t n, int lane) {
     uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
     if (lane < (int)head) dst[lane] = (uint8_t)byte;
@@ -697,7 +706,7 @@ __device__ __forceinline__ void zk_warp_fill(uint8_t* dst, uint32_t byte, uint32
 }
 
 // warp-cooperative match copy in HBM: dst[0..n) = dst[-off ..), overlap allowed (period doubling)
-__device__ __forceinline__ void zk_warp_match(uint8_t* dst, uint32_t off, uint32_t n, int lane) {
+__device__ __noinline__ void zk_warp_match(uint8_t* dst, uint32_t off, uint32_t n, int lane) {
     const uint8_t* src = dst - off;
     if (off >= n) { zk_warp_copy(dst, src, n, lane); return; }
     uint32_t have = off, done = 0;            // [src, src+have) is final periodic data
@@ -749,7 +758,7 @@ __device__ __forceinline__ void zk_ring_flush(const ZkRing& rg, uint32_t s, uint
 }
 
 // reload [s, e) HBM -> ring (after a direct HBM-to-HBM block)
-__device__ __forceinline__ void zk_ring_reload(const ZkRing& rg, uint32_t s, uint32_t e, int tid, int nthr) {
+__device__ __noinline__ void zk_ring_reload(const ZkRing& rg, uint32_t s, uint32_t e, int tid, int nthr) {
     if (e <= s) return;
     const uint32_t u0 = (s + rg.mis) >> 4, u1 = (e + rg.mis - 1) >> 4;
     for (uint32_t u = u0 + tid; u <= u1; u += nthr) {
@@ -1381,7 +1390,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     ws->prof.end(0, stream);
     // entropy stage: persistent warp-CTAs pulling groups of blocks from a work counter
     size_t est_blocks = (size_t)(total_d / ZK_BLOCK_MAX) + n;
-    const size_t seq_smem = sizeof(ZkSeqSlot) * ZK_SEQ_LANES, huf_smem = sizeof(ZkHufSlot) * ZK_HUF_SLOTS;
+    const size_t seq_smem = ((sizeof(ZkSeqTabs) + 15) & ~(size_t)15) + sizeof(ZkSeqSlot) * ZK_SEQ_LANES, huf_smem = sizeof(ZkHufSlot) * ZK_HUF_SLOTS;
     if (!ws->attr_set) {
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem + 65536));
