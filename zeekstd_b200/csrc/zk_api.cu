@@ -4,6 +4,7 @@
 #include "zk_ctx.h"
 #include "../../include/zeekstd_b200.h"
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <vector>
 
@@ -161,7 +162,7 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->slot[0].stream;
     const size_t sub_bytes = zk_env_size("ZK_DEV_SUB_BYTES", (size_t)1 << 30);
     ZkDecodeWs* ws = &c->slot[0].dws;
-    ws->share = 1;
+    ws->share = 1; ws->no_side = false;
     cudaEventRecord(c->ev0, st);
     int32_t worst = 0;
     for (uint32_t first = 0; first < n;) {
@@ -180,14 +181,15 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
 
 // ZK_E2E_TRACE=1: per-sub-batch timeline of the host-pointer paths (CUDA events on the slot streams), printed to stderr.
 struct ZkTrace {
-    bool on = false; cudaEvent_t t0 = nullptr; std::vector<cudaEvent_t> ev; std::vector<int> tag;
+    bool on = false; cudaEvent_t t0 = nullptr; std::vector<cudaEvent_t> ev; std::vector<int> tag; std::vector<double> host; double h0 = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
     void begin(cudaStream_t st) {
         on = getenv("ZK_E2E_TRACE") != nullptr; if (!on) return;
-        cudaEventCreate(&t0); cudaEventRecord(t0, st);
+        cudaEventCreate(&t0); cudaEventRecord(t0, st); h0 = now();
     }
     void mark(cudaStream_t st, int sub, int what) {
         if (!on) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(sub * 8 + what);
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(sub * 8 + what); host.push_back(now() - h0);
     }
     void end(const char* name) {
         if (!on) return;
@@ -195,7 +197,7 @@ struct ZkTrace {
         static const char* W[] = {"h2d0", "h2d1", "kern1", "d2h0", "d2h1"};
         for (size_t i = 0; i < ev.size(); i++) {
             float ms = 0; cudaEventElapsedTime(&ms, t0, ev[i]);
-            fprintf(stderr, "%s sub %d %s %.3f\n", name, tag[i] >> 3, W[tag[i] & 7], ms);
+            fprintf(stderr, "%s sub %d %s gpu %.3f host %.3f\n", name, tag[i] >> 3, W[tag[i] & 7], ms, host[i]);
             cudaEventDestroy(ev[i]);
         }
         cudaEventDestroy(t0);
@@ -216,6 +218,7 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     if (tr) tr->mark(s.stream, k, 0);
     ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
     if (tr) tr->mark(s.stream, k, 1);
+    s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 0) == 0;
     s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", (size_t)(zk_host_slots() + 1) / 2);
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
@@ -299,6 +302,7 @@ extern "C" int32_t zk_compress_frames_dev(zk_ctx* c, const void* d_src, size_t n
         const size_t in_off = (size_t)f0 * frame_size;
         const size_t in_len = n - in_off < (size_t)cnt * frame_size ? n - in_off : (size_t)cnt * frame_size;
         size_t produced = 0;
+        c->slot[0].ews.no_side = false;
         int rc = zk_encode_batch(&c->slot[0].ews, st, (const uint8_t*)d_src + in_off, in_len, frame_size, level, checksum,
                                  (uint8_t*)d_dst + out_pos, dst_cap - out_pos, c_sizes ? c_sizes + f0 : nullptr, cnt, &produced);
         if (rc) return rc;
@@ -369,6 +373,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         sub_k[si] = (int)k; tr.mark(s.stream, (int)k, 0);
         if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }
         tr.mark(s.stream, (int)k, 1);
+        s.ews.no_side = zk_env_size("ZK_HOST_SIDE", 0) == 0;
         rc = zk_encode_enqueue(&s.ews, s.stream, s.d_in, sb.in_len, frame_size, level, checksum, s.d_out, bound, sb.cnt);
         if (rc) { err = rc; break; }
         tr.mark(s.stream, (int)k, 2);

@@ -1402,21 +1402,25 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     if (need_s < gs) gs = (uint32_t)need_s;
     if (need_h < gh) gh = (uint32_t)need_h;
     // the two entropy kernels are independent: run the Huffman one on a side stream
-    if (!ws->side) {
-        ZK_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
-        ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_scan, cudaEventDisableTiming));
-        ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_huf, cudaEventDisableTiming));
+    cudaStream_t hs = stream;
+    if (!ws->no_side) {
+        if (!ws->side) {
+            ZK_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
+            ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_scan, cudaEventDisableTiming));
+            ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_huf, cudaEventDisableTiming));
+        }
+        hs = ws->side;
+        ZK_CUDA_OK(cudaEventRecord(ws->ev_scan, stream));
+        ZK_CUDA_OK(cudaStreamWaitEvent(hs, ws->ev_scan, 0));
     }
-    ZK_CUDA_OK(cudaEventRecord(ws->ev_scan, stream));
-    ZK_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_scan, 0));
-    ws->prof.begin(2, ws->side);
-    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem + ws->huf_pad, ws->side, a);
-    ws->prof.end(2, ws->side);
-    ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, ws->side));
+    ws->prof.begin(2, hs);
+    ZK_LAUNCH(zk_huf_kernel, gh, 32, huf_smem + ws->huf_pad, hs, a);
+    ws->prof.end(2, hs);
+    if (hs != stream) ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, hs));
     ws->prof.begin(1, stream);
     ZK_LAUNCH(zk_seq_kernel, gs, 32 * ZK_SEQ_WARPS, seq_smem, stream, a);
     ws->prof.end(1, stream);
-    ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_huf, 0));
+    if (hs != stream) ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_huf, 0));
     // exec stage: ring size / warps per entry chosen from how many entries share the machine
     // Each entry is one serial dependency chain, so throughput comes from entries in flight: pick warps per
     // CTA and ring size such that (if possible) every entry of the batch is resident at once.

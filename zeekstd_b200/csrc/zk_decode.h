@@ -29,6 +29,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     unsigned long long* trace = nullptr;
     int share = 1;                    // how many batches share the GPU concurrently (host pipeline depth)
     int prio = 0;                     // CUDA stream priority of the side stream (matches the slot's stream)
+    bool no_side = false;             // host pipelines: concurrency comes from the other sub-batches; every extra stream costs a hardware queue
     cudaStream_t side = nullptr; cudaEvent_t ev_scan = nullptr, ev_huf = nullptr;   // Huffman kernel runs beside the FSE kernel
     ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
     size_t want_blocks = 0, want_lit = 0, want_seq = 0;   // exact needs reported by a batch that overflowed

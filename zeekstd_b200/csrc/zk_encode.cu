@@ -630,12 +630,24 @@ __device__ int zkc_huf_build(ZkcC2Smem& sm, int lane) {
     int n = 0;
     for (int s0 = 0; s0 < 256; s0 += 32) n += __popc(__ballot_sync(0xFFFFFFFFu, sm.hist[s0 + lane] != 0));
     if (n < 2) return 0;
-    for (int s = lane; s < 256; s += 32) {
-        const uint32_t c = sm.hist[s];
-        if (!c) continue;
+    // compact the present symbols (ascending), then rank them among themselves: n^2 / 32 comparisons per lane instead of 256 * 8
+    uint32_t* pcnt = (uint32_t*)(sm.bitbuf + 4608);         // n x u32
+    uint8_t* psym = sm.bitbuf + 4608 + 1024;                // n x u8
+    {
+        int basep = 0;
+        for (int s0 = 0; s0 < 256; s0 += 32) {
+            const uint32_t c = sm.hist[s0 + lane];
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, c != 0);
+            if (c) { const int k = basep + __popc(m & ((1u << lane) - 1u)); pcnt[k] = c; psym[k] = (uint8_t)(s0 + lane); }
+            basep += __popc(m);
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+        const uint32_t c = pcnt[k];
         int rank = 0;
-        for (int j = 0; j < 256; j++) { const uint32_t cj = sm.hist[j]; rank += (cj != 0) && (cj < c || (cj == c && j < s)); }
-        order[rank] = (uint16_t)s;
+        for (int j = 0; j < n; j++) { const uint32_t cj = pcnt[j]; rank += (cj < c || (cj == c && j < k)); }
+        order[rank] = (uint16_t)psym[k];
     }
     __syncwarp();
     if (lane == 0) {
@@ -730,7 +742,7 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                 for (int s = 0; s <= last_sym; s++) if (sm.hlen[s]) cls[maxlen + 1 - sm.hlen[s]] += 1;
                 { uint32_t acc = 0; for (int w = 1; w <= maxlen; w++) { uint32_t n = cls[w]; cls[w] = acc; acc += n << (w - 1); } }
                 for (int s = 0; s <= last_sym; s++)
-                    if (sm.hlen[s]) { const int w = maxlen + 1 - sm.hlen[s]; sm.hcode[s] = (uint16_t)(cls[w] >> (w - 1)); cls[w] += 1u << (w - 1); }
+                    if (sm.hlen[s]) { const int w = maxlen + 1 - sm.hlen[s]; sm.hcode[s] = (uint16_t)((cls[w] >> (w - 1)) | ((uint32_t)sm.hlen[s] << 11)); cls[w] += 1u << (w - 1); }
                 // tree description: weights of symbols 0..last_sym-1 (the last one is implied)
                 int nw = last_sym;
                 for (int s = 0; s < nw; s++) sm.weights[s] = sm.hlen[s] ? (uint8_t)(maxlen + 1 - sm.hlen[s]) : 0;
@@ -813,17 +825,24 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                     for (uint32_t i = lane; i < words; i += 32) wbuf[i] = 0;
                     __syncwarp();
                     uint32_t base = 0;
-                    for (uint32_t g = 0; g < m; g += 32) {
-                        const uint32_t r = g + lane;                 // reversed index
-                        uint32_t l = 0, code = 0;
-                        if (r < m) { uint8_t sym = lits[s1 - 1 - r]; l = sm.hlen[sym]; code = sm.hcode[sym]; }
+                    for (uint32_t g = 0; g < m; g += 128) {
+                        // four symbols per lane (reversed indices r .. r+3, r lowest in the stream): one scan and at most
+                        // three atomics serve 128 symbols
+                        const uint32_t r = g + 4u * (uint32_t)lane;
+                        unsigned long long v = 0; uint32_t l = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (r + q < m) { const uint32_t cl = sm.hcode[lits[s1 - 1 - r - q]]; v |= (unsigned long long)(cl & 2047u) << l; l += cl >> 11; }
+                        }
                         uint32_t incl = l;
                         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
                         const uint32_t bitpos = base + incl - l;
                         if (l) {
-                            unsigned long long v = (unsigned long long)code << (bitpos & 31);
-                            atomicOr(&wbuf[bitpos >> 5], (uint32_t)v);
-                            if (v >> 32) atomicOr(&wbuf[(bitpos >> 5) + 1], (uint32_t)(v >> 32));
+                            const uint32_t sh = bitpos & 31u, w = bitpos >> 5;
+                            const unsigned long long lo = v << sh;
+                            atomicOr(&wbuf[w], (uint32_t)lo);
+                            if (lo >> 32) atomicOr(&wbuf[w + 1], (uint32_t)(lo >> 32));
+                            if (sh) { const uint32_t hi = (uint32_t)(v >> (64u - sh)); if (hi) atomicOr(&wbuf[w + 2], hi); }
                         }
                         base += __shfl_sync(0xFFFFFFFFu, incl, 31);
                     }
@@ -1111,18 +1130,21 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqWarp) * ZKC_SW;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
     // the two entropy kernels are independent and both latency-bound: run them side by side, join in zk_block_finish_kernel
-    if (!ws->side) {
-        ZKC_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
-        ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming));
-        ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming));
+    cudaStream_t ss = stream;
+    if (!ws->no_side) {
+        if (!ws->side) {
+            ZKC_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
+            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming));
+            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming));
+        }
+        ss = ws->side;
     }
     ws->prof.begin(6, stream);
-    ZKC_CUDA_OK(cudaEventRecord(ws->ev_a, stream));
-    ZKC_CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_a, 0));
-    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SW - 1) / ZKC_SW), 32 * ZKC_SW, seq_smem, ws->side, a);
-    ZKC_CUDA_OK(cudaEventRecord(ws->ev_b, ws->side));
+    if (ss != stream) { ZKC_CUDA_OK(cudaEventRecord(ws->ev_a, stream)); ZKC_CUDA_OK(cudaStreamWaitEvent(ss, ws->ev_a, 0)); }
+    ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SW - 1) / ZKC_SW), 32 * ZKC_SW, seq_smem, ss, a);
+    if (ss != stream) ZKC_CUDA_OK(cudaEventRecord(ws->ev_b, ss));
     ZK_LAUNCH(zk_lit_enc_kernel, (uint32_t)n_blocks, 32, 0, stream, a);
-    ZKC_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_b, 0));
+    if (ss != stream) ZKC_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_b, 0));
     ZK_LAUNCH(zk_block_finish_kernel, (uint32_t)((n_blocks + 3) / 4), 128, 0, stream, a);
     ws->prof.end(6, stream);
     ws->prof.begin(7, stream);
