@@ -100,6 +100,7 @@ extern "C" int32_t zk_ctx_create(int32_t device_ordinal, uint32_t flags, zk_ctx*
         c->slot[i].dws.sm_count = c->sm_count;
         c->slot[i].dws.ring_override = (uint32_t)zk_env_size("ZK_RING_BYTES", 0);   // tuning / tests: power of two >= 1024
         c->slot[i].dws.huf_pad = (uint32_t)zk_env_size("ZK_HUF_PAD", 0);
+        c->slot[i].dws.seq_ctas = (uint32_t)zk_env_size("ZK_SEQ_CTAS", 4); c->slot[i].dws.huf_ctas = (uint32_t)zk_env_size("ZK_HUF_CTAS", 5);
         c->slot[i].ews.sm_count = c->sm_count;
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
@@ -162,7 +163,7 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->slot[0].stream;
     const size_t sub_bytes = zk_env_size("ZK_DEV_SUB_BYTES", (size_t)1 << 30);
     ZkDecodeWs* ws = &c->slot[0].dws;
-    ws->share = 1; ws->no_side = false;
+    ws->share = 1; ws->no_side = zk_env_size("ZK_DEV_SIDE", 1) == 0;
     cudaEventRecord(c->ev0, st);
     int32_t worst = 0;
     for (uint32_t first = 0; first < n;) {
@@ -218,7 +219,7 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     if (tr) tr->mark(s.stream, k, 0);
     ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
     if (tr) tr->mark(s.stream, k, 1);
-    s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 0) == 0;
+    s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
     s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", (size_t)(zk_host_slots() + 1) / 2);
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
@@ -373,7 +374,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         sub_k[si] = (int)k; tr.mark(s.stream, (int)k, 0);
         if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }
         tr.mark(s.stream, (int)k, 1);
-        s.ews.no_side = zk_env_size("ZK_HOST_SIDE", 0) == 0;
+        s.ews.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
         rc = zk_encode_enqueue(&s.ews, s.stream, s.d_in, sb.in_len, frame_size, level, checksum, s.d_out, bound, sb.cnt);
         if (rc) { err = rc; break; }
         tr.mark(s.stream, (int)k, 2);

@@ -1397,7 +1397,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         ws->attr_set = true;
     }
-    uint32_t gs = (uint32_t)sms * 2, gh = (uint32_t)sms * 5;
+    uint32_t gs = (uint32_t)sms * ws->seq_ctas, gh = (uint32_t)sms * ws->huf_ctas;          // persistent CTAs: as many as fit (shared memory: 4 x 51 KiB, 5 x 41 KiB)
     size_t need_s = est_blocks / ZK_SEQ_LANES + 1, need_h = est_blocks / ZK_HUF_SLOTS + 1;
     if (need_s < gs) gs = (uint32_t)need_s;
     if (need_h < gh) gh = (uint32_t)need_h;

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
     if (len >= 16) {
         const uint32_t mflimit = hi32 - 8;                  // last position where 8 bytes can be read
         const uint32_t lt_mask = (1u << lane) - 1u;
+        const bool lazy = a.level >= 2;
         // pre-insert the history so matches can reach into the previous block
         if (a.level >= 2) {
             for (uint32_t p0 = 0; p0 < lo32; p0 += 32) {
@@ -167,19 +168,21 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
             }
             misses = 0;
             // take every non-overlapping match of this window, left to right (one memory round trip serves them all)
+            const uint32_t packed = (moff << 4) | mlen0;
             uint32_t next_lane = 0;
             bool cov = false;                               // this lane's byte is covered by a selected match
             while (next_lane < 32) {
                 const uint32_t m = found & (0xFFFFFFFFu << next_lane);
                 if (!m) break;
                 int f = __ffs((int)m) - 1;
-                uint32_t ml = __shfl_sync(0xFFFFFFFFu, mlen0, f);
+                uint32_t mo = __shfl_sync(0xFFFFFFFFu, packed, f);          // (offset << 4) | length
                 // one step of lazy matching: a clearly longer match starting at the next position wins (one more literal)
-                if (a.level >= 2 && ml < 8 && f < 31 && ((found >> (f + 1)) & 1u)) {
-                    const uint32_t ml2 = __shfl_sync(0xFFFFFFFFu, mlen0, f + 1);
-                    if (ml2 > ml + 1) { f++; ml = ml2; }
+                if (lazy && (mo & 15u) < 8 && f < 31 && ((found >> (f + 1)) & 1u)) {
+                    const uint32_t mo2 = __shfl_sync(0xFFFFFFFFu, packed, f + 1);
+                    if ((mo2 & 15u) > (mo & 15u) + 1) { f++; mo = mo2; }
                 }
-                const uint32_t off = __shfl_sync(0xFFFFFFFFu, moff, f);
+                uint32_t ml = mo & 15u;
+                const uint32_t off = mo >> 4;
                 const uint32_t mpos = wb + (uint32_t)f;
                 if (ml == 8) {
                     // extend cooperatively: lane k compares bytes [8 + 8k, 16 + 8k) of the match, 256 bytes a round
@@ -195,18 +198,16 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
                 }
                 // emit: literals [anchor, mpos) are already / will be placed by the windows that hold them
                 const uint32_t ll = mpos - anchor;
+                // after every sequence r0 == off; a repeat of r0 itself (ll != 0) leaves the history alone, every other
+                // case shifts (r0 -> r1) and drops r2, except the r1 hit, which swaps the first two
                 uint32_t ov = off + 3;
+                bool hit0 = false, hit1 = false;
                 if (known == 3) {
-                    if (ll != 0) { if (off == r0) ov = 1; else if (off == r1) ov = 2; else if (off == r2) ov = 3; }
-                    else { if (off == r1) ov = 1; else if (off == r2) ov = 2; else if (r0 > 1 && off == r0 - 1) ov = 3; }
-                }
-                if (ov > 3) { r2 = r1; r1 = r0; r0 = off; if (known < 3) known++; }
-                else {
-                    const uint32_t idx = ov - 1 + (ll == 0);
-                    if (idx == 1) { const uint32_t t = r1; r1 = r0; r0 = t; }
-                    else if (idx == 2) { const uint32_t t = r2; r2 = r1; r1 = r0; r0 = t; }
-                    else if (idx == 3) { const uint32_t t = r0 - 1; r2 = r1; r1 = r0; r0 = t; }
-                }
+                    const bool e0 = off == r0, e1 = off == r1, e2 = off == r2, em = r0 > 1 && off == r0 - 1;
+                    if (ll != 0) { if (e0) { ov = 1; hit0 = true; } else if (e1) { ov = 2; hit1 = true; } else if (e2) ov = 3; }
+                    else { if (e1) { ov = 1; hit1 = true; } else if (e2) ov = 2; else if (em) ov = 3; }
+                } else known++;
+                if (!hit0) { r2 = hit1 ? r2 : r1; r1 = r0; r0 = off; }
                 if (lane == (int)(nseq & 31u)) { s_ll = ll; s_ml = ml - 3; s_off = ov; }
                 if ((nseq & 31u) == 31u) {
                     const uint32_t at = nseq - 31u + (uint32_t)lane;
