@@ -874,8 +874,8 @@ __device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint3
     }
 }
 
-__global__ void __launch_bounds__(512, 1) zk_exec_kernel(ZkDecodeArgs a, uint32_t ring_bytes) {
-    __shared__ ZkD2Smem sm;
+template <int VARIANT>
+__device__ __forceinline__ void zk_exec_body(ZkD2Smem& sm, const ZkDecodeArgs& a, uint32_t ring_bytes) {
     ZK_DYN_SMEM(ring_mem);
     const uint32_t e = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
@@ -1204,6 +1204,18 @@ __global__ void __launch_bounds__(512, 1) zk_exec_kernel(ZkDecodeArgs a, uint32_
     }
 }
 
+// Two register budgets for the same body: up to 16 warps per entry (<= 128 registers, few entries per SM), and a
+// 5-warp variant compiled for 4 CTAs per SM (<= 102 registers) for large batches, where every entry of the batch should
+// stay resident and the warps per SM are what hides the latency.
+__global__ void __launch_bounds__(512, 1) zk_exec_kernel(ZkDecodeArgs a, uint32_t ring_bytes) {
+    __shared__ ZkD2Smem sm;
+    zk_exec_body<0>(sm, a, ring_bytes);
+}
+__global__ void __launch_bounds__(160, 4) zk_exec_kernel_w5(ZkDecodeArgs a, uint32_t ring_bytes) {
+    __shared__ ZkD2Smem sm;
+    zk_exec_body<1>(sm, a, ring_bytes);
+}
+
 // =============================================================================================
 // K-D3: XXH64 content checksum (A.8), one warp per entry, lanes 0..3 carry the four accumulators
 // =============================================================================================
@@ -1395,6 +1407,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem + 65536));
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel_w5, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         ws->attr_set = true;
     }
     uint32_t gs = (uint32_t)sms * ws->seq_ctas, gh = (uint32_t)sms * ws->huf_ctas;          // persistent CTAs: as many as fit (shared memory: 4 x 51 KiB, 5 x 41 KiB)
@@ -1427,13 +1440,20 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     // (`share` > 1: that many sub-batches of a host pipeline run concurrently on different streams)
     int per_sm = (int)(((unsigned long long)n * (unsigned)(ws->share > 0 ? ws->share : 1) + (uint32_t)sms - 1) / (uint32_t)sms);
     int W = exec_warps;
-    if (W <= 0) { W = 18 / per_sm; if (W < 2) W = 2; }     // 113 registers/thread -> 18 warps per SM: keep every entry of the batch resident
+    // 126 registers/thread -> 16 warps per SM; from four entries per SM on, the 96-register build of the same body
+    // (20 warps per SM, <= 5 per entry) keeps every entry of the batch resident with one more warp each
+    bool small_regs = false;
+    if (W <= 0) {
+        if (per_sm >= 4) { W = 20 / per_sm; if (W < 2) W = 2; small_regs = true; }
+        else W = 16 / per_sm;
+    } else small_regs = W <= 5 && per_sm >= 4;
     if (W > 16) W = 16;
     uint32_t ring = 128 * 1024;
     while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;
     if (ws->ring_override) ring = ws->ring_override;
     ws->prof.begin(3, stream);
-    ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
+    if (small_regs) ZK_LAUNCH(zk_exec_kernel_w5, n, W * 32, ring, stream, a, ring);
+    else ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
     ws->prof.end(3, stream);
     if (verify_checksum) { ws->prof.begin(4, stream); ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a); ws->prof.end(4, stream); }
     ZK_CUDA_OK(cudaMemcpyAsync(ws->h_entries, ws->entries, (size_t)n * sizeof(ZkEntry), cudaMemcpyDeviceToHost, stream));
