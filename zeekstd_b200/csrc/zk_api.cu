@@ -14,14 +14,19 @@
 #define ZK_RT_OK(x) do { (void)(x); } while (0)
 #endif
 
-static int zk_host_slots();
+static int zk_host_slots(bool enc);
 static size_t zk_env_size(const char* name, size_t dflt) {
     const char* s = getenv(name);
     if (!s || !*s) return dflt;
     return (size_t)strtoull(s, nullptr, 10);
 }
 
-static int zk_host_slots() { size_t v = zk_env_size("ZK_HOST_SLOTS", 6); return (int)(v < 1 ? 1 : (v > ZK_SLOTS ? ZK_SLOTS : v)); }
+// sub-batches in flight of the host-pointer pipelines (measured on B200, tools/e2e_sweep4.sh): decompress wants many
+// (its exec stage is latency-bound per frame), compress few (its kernels fill the machine from one 128 MiB sub-batch)
+static int zk_host_slots(bool enc) {
+    size_t v = zk_env_size(enc ? "ZK_HOST_SLOTS_ENC" : "ZK_HOST_SLOTS", enc ? 4 : 8);
+    return (int)(v < 1 ? 1 : (v > ZK_SLOTS ? ZK_SLOTS : v));
+}
 
 extern "C" const char* zk_version(void) {
 #ifdef ZK_EMUL
@@ -100,7 +105,7 @@ extern "C" int32_t zk_ctx_create(int32_t device_ordinal, uint32_t flags, zk_ctx*
         c->slot[i].dws.sm_count = c->sm_count;
         c->slot[i].dws.ring_override = (uint32_t)zk_env_size("ZK_RING_BYTES", 0);   // tuning / tests: power of two >= 1024
         c->slot[i].dws.huf_pad = (uint32_t)zk_env_size("ZK_HUF_PAD", 0);
-        c->slot[i].dws.seq_ctas = (uint32_t)zk_env_size("ZK_SEQ_CTAS", 4); c->slot[i].dws.huf_ctas = (uint32_t)zk_env_size("ZK_HUF_CTAS", 5);
+        c->slot[i].dws.seq_ctas = (uint32_t)zk_env_size("ZK_SEQ_CTAS", 4); c->slot[i].dws.huf_ctas = (uint32_t)zk_env_size("ZK_HUF_CTAS", 8);
         c->slot[i].ews.sm_count = c->sm_count;
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
@@ -220,7 +225,7 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
     if (tr) tr->mark(s.stream, k, 1);
     s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
-    s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", (size_t)(zk_host_slots() + 1) / 2);
+    s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", 3);
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
     if (rc) return rc;
@@ -253,7 +258,7 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
     ZK_RT_OK(cudaSetDevice(c->device));
     const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);     // measured best on B200 (tools/e2e_sweep2.sh)
     ZkSubDec sub[ZK_SLOTS];
-    const int NS = zk_host_slots();
+    const int NS = zk_host_slots(false);
     int32_t worst = 0;
     uint32_t k = 0;
     ZkTrace tr; tr.begin(c->slot[0].stream);
@@ -355,7 +360,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         return 0;
     };
     uint32_t k = 0;
-    const int NS = zk_host_slots();
+    const int NS = zk_host_slots(true);
     int order[ZK_SLOTS]; int n_inflight = 0;              // completion must follow submission order
     for (uint32_t f0 = 0; f0 < nf && !err; f0 += per, k++) {
         const int si = (int)(k % NS);

@@ -412,10 +412,16 @@ __global__ void __launch_bounds__(32 * ZK_SEQ_WARPS) zk_seq_kernel(ZkDecodeArgs 
 // =============================================================================================
 // K-D1h: Huffman literal decode -- one LANE per Huffman stream (4 lanes per 4-stream block).
 // =============================================================================================
-#define ZK_HUF_SLOTS 8            // blocks per warp-CTA; 8 x 5.2 KiB -> 5 CTAs / SM
+#define ZK_HUF_SLOTS 8            // blocks per warp-CTA; 8 x 3.1 KiB -> 9 CTAs / SM
 
+// Two-level decoding table.  Cells are laid out weight ascending (A.4), so the codes of the two longest lengths occupy
+// the first L <= 510 cells of the 2^maxBits index space, and everything above is replicated at least four times:
+//   idx < L  -> low[idx]        (full resolution)        idx >= L -> l1[idx >> 2]      (2^(maxBits-2) <= 512 entries)
+// 2 KiB instead of the flat 4 KiB table: the kernel is bound by memory latency with shared memory capping the streams
+// in flight, so the extra compare per symbol buys 1.7x the blocks per SM.
 struct ZkHufSlot {
-    uint16_t tbl[2048];                        // (nbBits << 8) | symbol
+    uint16_t l1[512], low[512];                // (nbBits << 8) | symbol
+    uint32_t n_low;                            // L
     uint8_t weights[256];
     uint16_t hpos[256];
     uint8_t wsym[64], wnb[64]; uint16_t wbase[64];   // FSE table for compressed weights (log <= 6)
@@ -485,26 +491,29 @@ __device__ uint32_t zk_read_huf_weights(ZkHufSlot& sl, const uint8_t* p, uint32_
 }
 
 // Decode `cnt` Huffman symbols of one stream into out (A.4).  Returns false on corruption.
-__device__ bool zk_huf_decode_stream(const uint16_t* tbl, int max_bits, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t cnt) {
+__device__ __forceinline__ uint32_t zk_huf_lookup(const ZkHufSlot& sl, uint32_t idx) {
+    return idx < sl.n_low ? sl.low[idx & 511u] : sl.l1[idx >> 2];
+}
+__device__ bool zk_huf_decode_stream(const ZkHufSlot& sl, int max_bits, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t cnt) {
     ZkBackBits br;
     if (!br.init(p, n)) return false;
     uint32_t i = 0;
     while (i < cnt && ((uintptr_t)(out + i) & 3)) {
         br.refill();
-        uint32_t e = tbl[br.peek(max_bits)]; br.skip((int)(e >> 8)); out[i++] = (uint8_t)e;
+        uint32_t e = zk_huf_lookup(sl, br.peek(max_bits)); br.skip((int)(e >> 8)); out[i++] = (uint8_t)e;
     }
     for (; i + 4 <= cnt; i += 4) {
         br.refill();                                   // >= 33 bits: three codes of <= 11 bits
-        uint32_t e0 = tbl[br.peek(max_bits)]; br.skip((int)(e0 >> 8));
-        uint32_t e1 = tbl[br.peek(max_bits)]; br.skip((int)(e1 >> 8));
-        uint32_t e2 = tbl[br.peek(max_bits)]; br.skip((int)(e2 >> 8));
+        uint32_t e0 = zk_huf_lookup(sl, br.peek(max_bits)); br.skip((int)(e0 >> 8));
+        uint32_t e1 = zk_huf_lookup(sl, br.peek(max_bits)); br.skip((int)(e1 >> 8));
+        uint32_t e2 = zk_huf_lookup(sl, br.peek(max_bits)); br.skip((int)(e2 >> 8));
         br.refill();
-        uint32_t e3 = tbl[br.peek(max_bits)]; br.skip((int)(e3 >> 8));
+        uint32_t e3 = zk_huf_lookup(sl, br.peek(max_bits)); br.skip((int)(e3 >> 8));
         *(uint32_t*)(out + i) = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | ((e3 & 0xFF) << 24);
     }
     for (; i < cnt; i++) {
         br.refill();
-        uint32_t e = tbl[br.peek(max_bits)]; br.skip((int)(e >> 8)); out[i] = (uint8_t)e;
+        uint32_t e = zk_huf_lookup(sl, br.peek(max_bits)); br.skip((int)(e >> 8)); out[i] = (uint8_t)e;
     }
     return br.bp == 0;
 }
@@ -550,6 +559,8 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
                 for (int w = 1; w <= sl.huf_bits; w++) { rank_start[w] = acc; acc += cntw[w] << (w - 1); }
                 for (int s = 0; s < sl.nw; s++) { int w = sl.weights[s]; if (w) { sl.hpos[s] = (uint16_t)rank_start[w]; rank_start[w] += 1u << (w - 1); } }
                 if (acc != (1u << sl.huf_bits)) st = ZKZ_CORRUPTION;
+                sl.n_low = cntw[1] + 2u * cntw[2];                 // cells of the two longest code lengths (<= 512)
+                if (sl.n_low > 512u) st = ZKZ_CORRUPTION;
             }
             sl.st = st; sl.tree_bytes = tb;
         }
@@ -563,7 +574,8 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
                 if (!w) continue;
                 uint32_t len = 1u << (w - 1), pos = sl.hpos[s];
                 uint16_t e = (uint16_t)(((max_bits + 1 - w) << 8) | s);
-                for (uint32_t i = 0; i < len; i++) sl.tbl[pos + i] = e;
+                if (w <= 2) for (uint32_t i = 0; i < len; i++) sl.low[pos + i] = e;
+                else for (uint32_t i = 0; i < (len >> 2); i++) sl.l1[(pos >> 2) + i] = e;
             }
         }
         __syncwarp();
@@ -574,7 +586,7 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
             uint32_t qn = lh.comp - sl.tree_bytes;
             uint8_t* out = a.lit + blk.lit_base;
             if (lh.streams == 1) {
-                if (stream == 0) ok = zk_huf_decode_stream(sl.tbl, sl.huf_bits, q, qn, out, lh.regen);
+                if (stream == 0) ok = zk_huf_decode_stream(sl, sl.huf_bits, q, qn, out, lh.regen);
             } else {
                 uint32_t seg = (lh.regen + 3) / 4;
                 if (qn < 10 || lh.regen < 6 || seg * 3 > lh.regen) ok = false;   // jump table + 4 non-empty streams; libzstd rejects regen < 6
@@ -586,7 +598,7 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
                         uint32_t off = stream == 0 ? 0 : (stream == 1 ? s1 : (stream == 2 ? s1 + s2 : s1 + s2 + s3));
                         uint32_t len = stream == 0 ? s1 : (stream == 1 ? s2 : (stream == 2 ? s3 : s4));
                         uint32_t cnt = stream < 3 ? seg : lh.regen - 3 * seg;
-                        ok = zk_huf_decode_stream(sl.tbl, sl.huf_bits, q + 6 + off, len, out + stream * seg, cnt);
+                        ok = zk_huf_decode_stream(sl, sl.huf_bits, q + 6 + off, len, out + stream * seg, cnt);
                     }
                 }
             }

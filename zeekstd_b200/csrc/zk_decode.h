@@ -29,7 +29,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     unsigned long long* trace = nullptr;
     int share = 1;                    // how many batches share the GPU concurrently (host pipeline depth)
     int prio = 0;                     // CUDA stream priority of the side stream (matches the slot's stream)
-    uint32_t seq_ctas = 4, huf_ctas = 5;   // persistent CTAs per SM of the two entropy kernels (tuning: ZK_SEQ_CTAS / ZK_HUF_CTAS)
+    uint32_t seq_ctas = 4, huf_ctas = 8;   // persistent CTAs per SM of the two entropy kernels (tuning: ZK_SEQ_CTAS / ZK_HUF_CTAS)
     bool no_side = false;             // host pipelines: concurrency comes from the other sub-batches; every extra stream costs a hardware queue
     cudaStream_t side = nullptr; cudaEvent_t ev_scan = nullptr, ev_huf = nullptr;   // Huffman kernel runs beside the FSE kernel
     ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
