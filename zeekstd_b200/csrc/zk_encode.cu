@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         // frame starts from the known {1,4,8}.  o_off receives Offset_Values (1..3 = repeat codes, offset + 3 otherwise).
         uint32_t r0 = 1, r1 = 4, r2 = 8, known = lo == fstart ? 3u : 0u;
         uint32_t misses = 0;                                // consecutive windows without a match: widen the stride (incompressible data)
-        uint32_t s_ll = 0, s_ml = 0, s_off = 0;             // staged sequence (slot nseq & 31 lives in that lane)
+        uint32_t s_ll = 0, s_ml = 0, s_off = 0, flushed = 0; // staged sequences: slot nseq - flushed lives in that lane
         for (;;) {
             const uint32_t stride = 1u + min(misses >> 3, 3u);
             if (ip + 32u * stride > mflimit) {
@@ -169,6 +169,11 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
             misses = 0;
             // take every non-overlapping match of this window, left to right (one memory round trip serves them all)
             const uint32_t packed = (moff << 4) | mlen0;
+            // a stride-1 window yields at most 8 sequences (matches are >= 4 bytes): make room in the 32 staging lanes first
+            if (nseq - flushed > 24u) {
+                if ((uint32_t)lane < nseq - flushed) { const uint32_t at = flushed + (uint32_t)lane; o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off; }
+                flushed = nseq;
+            }
             uint32_t next_lane = 0;
             bool cov = false;                               // this lane's byte is covered by a selected match
             while (next_lane < 32) {
@@ -201,18 +206,18 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
                 // after every sequence r0 == off; a repeat of r0 itself (ll != 0) leaves the history alone, every other
                 // case shifts (r0 -> r1) and drops r2, except the r1 hit, which swaps the first two
                 uint32_t ov = off + 3;
-                bool hit0 = false, hit1 = false;
-                if (known == 3) {
-                    const bool e0 = off == r0, e1 = off == r1, e2 = off == r2, em = r0 > 1 && off == r0 - 1;
-                    if (ll != 0) { if (e0) { ov = 1; hit0 = true; } else if (e1) { ov = 2; hit1 = true; } else if (e2) ov = 3; }
-                    else { if (e1) { ov = 1; hit1 = true; } else if (e2) ov = 2; else if (em) ov = 3; }
-                } else known++;
-                if (!hit0) { r2 = hit1 ? r2 : r1; r1 = r0; r0 = off; }
-                if (lane == (int)(nseq & 31u)) { s_ll = ll; s_ml = ml - 3; s_off = ov; }
-                if ((nseq & 31u) == 31u) {
-                    const uint32_t at = nseq - 31u + (uint32_t)lane;
-                    o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off;
+                if (off != r0 && off != r1 && off != r2 && off + 1 != r0) {           // the common case: an explicit offset
+                    r2 = r1; r1 = r0; r0 = off; known += known < 3;
+                } else {
+                    bool hit0 = false, hit1 = false;
+                    if (known == 3) {
+                        const bool e0 = off == r0, e1 = off == r1, e2 = off == r2, em = r0 > 1 && off == r0 - 1;
+                        if (ll != 0) { if (e0) { ov = 1; hit0 = true; } else if (e1) { ov = 2; hit1 = true; } else if (e2) ov = 3; }
+                        else { if (e1) { ov = 1; hit1 = true; } else if (e2) ov = 2; else if (em) ov = 3; }
+                    } else known++;
+                    if (!hit0) { r2 = hit1 ? r2 : r1; r1 = r0; r0 = off; }
                 }
+                if (lane == (int)(nseq - flushed)) { s_ll = ll; s_ml = ml - 3; s_off = ov; }
                 nseq++;
                 cov = cov || (p - mpos < ml);               // unsigned: mpos <= p < mpos + ml
                 anchor = mpos + ml; rep = off;
@@ -223,8 +228,8 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
             nlit += (uint32_t)__popc(lm);
             ip = anchor > wb + 32u ? anchor : wb + 32u;
         }
-        if (lane < (int)(nseq & 31u)) {
-            const uint32_t at = (nseq & ~31u) + (uint32_t)lane;
+        if ((uint32_t)lane < nseq - flushed) {
+            const uint32_t at = flushed + (uint32_t)lane;
             o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off;
         }
     }
