@@ -336,7 +336,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
     const uint32_t nf = zk_frames_of(n, frame_size);
     if (nf > frames_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
     ZK_RT_OK(cudaSetDevice(c->device));
-    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES_ENC", (size_t)128 << 20);   // measured best on B200 (tools/e2e_sweep2.sh)
+    const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES_ENC", (size_t)96 << 20);    // measured best on B200 (tools/knobs_round.sh)
     uint32_t per = (uint32_t)(sub_bytes / frame_size); if (per == 0) per = 1;
     // The compressed size of a sub-batch is only known when it completes, so output positions are assigned in
     // order at completion time: H2D and kernels of later sub-batches overlap the D2H of earlier ones.

@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(32 * ZKC_SW) zk_seq_enc_kernel(ZkEncodeArgs a)
 
 struct ZkcC2Smem {
     uint32_t hist[256];
+    uint32_t hist4[2][256];             // per-stream counts, two 16-bit fields per word (streams 0|1, 2|3): stream sizes without a second pass over the literals
     uint16_t hcode[256]; uint8_t hlen[256];
     uint8_t bitbuf[ZKC_BITBUF];
     ZkcFse fse[1];                      // FSE table for the Huffman weights
@@ -716,9 +717,25 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
 
     // ------------------------------------------------------------------ literals section (A.3)
     if (!raw_block) {
-        for (int i = lane; i < 256; i += 32) { sm.hist[i] = 0; sm.hlen[i] = 0; }
+        for (int i = lane; i < 256; i += 32) { sm.hist4[0][i] = 0; sm.hist4[1][i] = 0; sm.hlen[i] = 0; }
         __syncwarp();
-        for (uint32_t i = lane; i < nlit; i += 32) atomicAdd(&sm.hist[lits[i]], 1u);
+        {   // four literals per lane and load (the buffer is 32 KiB aligned); the stream a literal belongs to follows from its index
+            const uint32_t seg = (nlit + 3) / 4, n4 = nlit & ~3u;
+            for (uint32_t i = 4u * (uint32_t)lane; i < n4; i += 128) {
+                const uint32_t w = *(const uint32_t*)(lits + i);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t idx = i + q, st = (idx >= seg) + (idx >= 2 * seg) + (idx >= 3 * seg);
+                    atomicAdd(&sm.hist4[st >> 1][(w >> (8 * q)) & 255u], 1u << ((st & 1u) * 16u));
+                }
+            }
+            if ((uint32_t)lane < nlit - n4) {
+                const uint32_t idx = n4 + lane, st = (idx >= seg) + (idx >= 2 * seg) + (idx >= 3 * seg);
+                atomicAdd(&sm.hist4[st >> 1][lits[idx]], 1u << ((st & 1u) * 16u));
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) { const uint32_t a0 = sm.hist4[0][i], a1 = sm.hist4[1][i]; sm.hist[i] = (a0 & 0xFFFFu) + (a0 >> 16) + (a1 & 0xFFFFu) + (a1 >> 16); }
         __syncwarp();
         // decide: Raw / RLE / Huffman
         int maxlen = 0; uint32_t lit_mode = 0;           // 0 raw, 1 rle, 2 huffman
@@ -798,12 +815,17 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
             // stream sizes first (so the section header, which precedes the streams, can be sized)
             const uint32_t seg = (nlit + 3) / 4;
             uint32_t ssz[4];
-            for (int st = 0; st < 4; st++) {
-                uint32_t s0 = st * seg, s1 = st < 3 ? s0 + seg : nlit;
-                uint32_t bits = 0;
-                for (uint32_t i = s0 + lane; i < s1; i += 32) bits += sm.hlen[lits[i]];
-                for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
-                ssz[st] = (bits + 1 + 7) / 8;            // + end mark
+            {
+                uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+                for (int sy = lane; sy < 256; sy += 32) {
+                    const uint32_t l = sm.hlen[sy], a0 = sm.hist4[0][sy], a1 = sm.hist4[1][sy];
+                    b0 += (a0 & 0xFFFFu) * l; b1 += (a0 >> 16) * l; b2 += (a1 & 0xFFFFu) * l; b3 += (a1 >> 16) * l;
+                }
+                for (int d = 16; d; d >>= 1) {
+                    b0 += __shfl_xor_sync(0xFFFFFFFFu, b0, d); b1 += __shfl_xor_sync(0xFFFFFFFFu, b1, d);
+                    b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, d); b3 += __shfl_xor_sync(0xFFFFFFFFu, b3, d);
+                }
+                ssz[0] = (b0 + 1 + 7) / 8; ssz[1] = (b1 + 1 + 7) / 8; ssz[2] = (b2 + 1 + 7) / 8; ssz[3] = (b3 + 1 + 7) / 8;   // + end mark
             }
             const uint32_t comp = tree_bytes + 6 + ssz[0] + ssz[1] + ssz[2] + ssz[3];
             if (comp >= nlit || ssz[0] > 0xFFFF || ssz[1] > 0xFFFF || ssz[2] > 0xFFFF) lit_mode = 0;
