@@ -18,7 +18,8 @@
 #include <string.h>
 
 #define ZKC_BLOCK 32768u                 // zstd block size used by this encoder (<= Block_Maximum_Size)
-#define ZKC_HLOG 12                      // hash table: 4096 x u16 per warp
+#define ZKC_HLOG_FAST 11                 // hash table per warp: 2048 x u16 at level 1 (36 warps / SM hide the two dependent loads per window),
+#define ZKC_HLOG 12                      // 4096 x u16 from level 2 on (24 warps / SM, 0.3-3 % better ratio)
 #define ZKC_MINMATCH 5
 #define ZKC_MAXSEQ (ZKC_BLOCK / 4 + 8)   // every sequence covers at least 4 bytes (repeat matches may be 4 long); multiple of 8 for 16-byte chunked loads
 #define ZKC_SLOT (ZKC_BLOCK + 64u)       // per-block staging slot for the compressed block
@@ -63,8 +64,9 @@ __device__ __forceinline__ unsigned long long zkc_ld8(const uint8_t* p) {
     uint32_t w2 = q[2], sh = mis * 8;
     return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
 }
+template <int HLOG>
 __device__ __forceinline__ uint32_t zkc_hash5(unsigned long long v) {
-    return (uint32_t)(((v << 24) * 889523592379ull) >> (64 - ZKC_HLOG));
+    return (uint32_t)(((v << 24) * 889523592379ull) >> (64 - HLOG));
 }
 
 // =============================================================================================
@@ -79,8 +81,9 @@ __device__ __forceinline__ uint32_t zkc_hash5(unsigned long long v) {
 // =============================================================================================
 #define ZKC_C1_WARPS 4
 
+template <int HLOG>
 __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArgs a) {
-    __shared__ uint16_t tables[ZKC_C1_WARPS][1 << ZKC_HLOG];
+    __shared__ uint16_t tables[ZKC_C1_WARPS][1 << HLOG];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * ZKC_C1_WARPS + warp;
     if (b >= a.n_blocks) return;
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
     const size_t base = lo - fstart >= ZKC_BLOCK ? lo - ZKC_BLOCK : fstart;
     const uint8_t* sb = a.src + base;
     const uint32_t lo32 = (uint32_t)(lo - base), hi32 = (uint32_t)(hi - base);
-    for (int i = lane; i < (1 << ZKC_HLOG); i += 32) table[i] = 0;
+    for (int i = lane; i < (1 << HLOG); i += 32) table[i] = 0;
     __syncwarp();
     const uint32_t len = hi32 - lo32;
     uint16_t* o_ll = a.seq_ll + (size_t)b * ZKC_MAXSEQ; uint16_t* o_ml = a.seq_ml + (size_t)b * ZKC_MAXSEQ;
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         if (a.level >= 2) {
             for (uint32_t p0 = 0; p0 < lo32; p0 += 32) {
                 const uint32_t p = p0 + lane;
-                const uint32_t hh = p < lo32 ? zkc_hash5(zkc_ld8(sb + p)) : (0xFFFF0000u | (uint32_t)lane);
+                const uint32_t hh = p < lo32 ? zkc_hash5<HLOG>(zkc_ld8(sb + p)) : (0xFFFF0000u | (uint32_t)lane);
                 const uint32_t same = __match_any_sync(0xFFFFFFFFu, hh);
                 if (p < lo32 && lane == 31 - __clz((int)same)) table[hh] = (uint16_t)p;
             }
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
             const uint32_t p = wb + (uint32_t)lane * stride;
             if (lane < 2) zk_prefetch_l1(sb + min(wb + 256u + 128u * (uint32_t)lane, hi32 - 1u));
             const unsigned long long cur = zkc_ld8(sb + p);
-            const uint32_t h = zkc_hash5(cur);
+            const uint32_t h = zkc_hash5<HLOG>(cur);
             const uint32_t cand = table[h];
             __syncwarp();
             // several lanes may hash to the same slot: the highest position wins, as sequential insertion would leave it
@@ -858,9 +861,20 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                         // three atomics serve 128 symbols
                         const uint32_t r = g + 4u * (uint32_t)lane;
                         unsigned long long v = 0; uint32_t l = 0;
+                        if (r + 4 <= m) {
+                            // the four symbols are the bytes [s1-4-r, s1-r): one unaligned 4-byte load (two aligned ones)
+                            const uint32_t ad = s1 - 4u - r, mis = ad & 3u;
+                            const uint32_t* wp = (const uint32_t*)(lits + (ad - mis));
+                            const uint32_t w4 = mis ? __funnelshift_r(wp[0], wp[1], mis * 8u) : wp[0];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            if (r + q < m) { const uint32_t cl = sm.hcode[lits[s1 - 1 - r - q]]; v |= (unsigned long long)(cl & 2047u) << l; l += cl >> 11; }
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t cl = sm.hcode[(w4 >> (8 * (3 - q))) & 255u]; v |= (unsigned long long)(cl & 2047u) << l; l += cl >> 11;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                if (r + q < m) { const uint32_t cl = sm.hcode[lits[s1 - 1 - r - q]]; v |= (unsigned long long)(cl & 2047u) << l; l += cl >> 11; }
+                            }
                         }
                         uint32_t incl = l;
                         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
@@ -1153,7 +1167,8 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     a.dst = d_dst; a.dst_cap = dst_cap; a.total = (unsigned long long*)(base + o_tot); a.error = (uint32_t*)(base + o_tot + 8);
     ZKC_CUDA_OK(cudaMemsetAsync(base + o_tot, 0, 16, stream));
     ws->prof.begin(5, stream);
-    ZK_LAUNCH(zk_match_kernel, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
+    if (a.level <= 1) ZK_LAUNCH(zk_match_kernel<ZKC_HLOG_FAST>, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
+    else ZK_LAUNCH(zk_match_kernel<ZKC_HLOG>, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
     ws->prof.end(5, stream);
     const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqWarp) * ZKC_SW;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
