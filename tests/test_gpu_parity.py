@@ -60,6 +60,19 @@ def test_compress_edge_sizes(ctx):
         cases.check_compress_roundtrip(ctx, x[:n], fs, 3, n % 2 == 0)
 
 
+def test_compress_high_entropy_literals(ctx):
+    """literal-heavy blocks: Huffman streams longer than the encoder's shared-memory buffer take the tiled packer,
+    and the decoder sees 11-bit two-level tables with many long codes"""
+    rng = np.random.default_rng(5)
+    for k, level in ((64, 1), (128, 3), (200, 1), (250, 3)):
+        cases.check_compress_roundtrip(ctx, rng.integers(0, k, 3 << 20, dtype=np.uint8), 1 << 20, level, k % 3 == 0)
+    # skewed: a few very frequent symbols and a long tail of rare ones (deep trees, length-limited to 11 bits)
+    p = 1.0 / np.arange(1, 257) ** 1.3; p /= p.sum()
+    x = rng.choice(256, size=3 << 20, p=p).astype(np.uint8)
+    cases.check_compress_roundtrip(ctx, x, 1 << 20, 1, True)
+    cases.check_decode_matches_libzstd(ctx, x, 1 << 20, 3, True)
+
+
 def test_compress_is_deterministic(ctx):
     x = corpus.make_mix(8 << 20, seed=3).numpy()
     a = ctx.compress_frames(x, 1 << 20, 1, True)[0].tobytes()

@@ -46,6 +46,17 @@ def test_compress_edge_sizes(ctx):
         cases.check_compress_roundtrip(ctx, x[:n], fs, 3, True)
 
 
+def test_compress_high_entropy_literals(ctx):
+    """Huffman streams longer than the encoder's shared-memory buffer (tiled packer); deep, length-limited trees"""
+    rng = np.random.default_rng(5)
+    for k, level in ((64, 1), (128, 3), (200, 1)):
+        cases.check_compress_roundtrip(ctx, rng.integers(0, k, 70_000, dtype=np.uint8), 1 << 20, level, k % 3 == 0)
+    p = 1.0 / np.arange(1, 257) ** 1.3; p /= p.sum()
+    x = rng.choice(256, size=70_000, p=p).astype(np.uint8)
+    cases.check_compress_roundtrip(ctx, x, 1 << 20, 1, True)
+    cases.check_decode_matches_libzstd(ctx, x, 1 << 20, 3, True)
+
+
 def test_golden_archives(ctx):
     cases.check_golden_archives(ctx)
 

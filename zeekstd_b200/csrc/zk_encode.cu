@@ -615,17 +615,20 @@ __global__ void __launch_bounds__(32 * ZKC_SW) zk_seq_enc_kernel(ZkEncodeArgs a)
     if (lane == 0) { a.blocks[b].seq_hdr = hb; a.blocks[b].seq_bits = sb; }
 }
 
-#define ZKC_BITBUF 12288u               // shared-memory bit buffer: one Huffman stream (<= 8192 symbols x 11 bits) or the sequence bitstream
+#define ZKC_BITBUF 6144u                // shared-memory scratch: Huffman build arrays, then one Huffman stream (longer streams are packed in tiles)
 
+// per-warp shared state of K-C2l.  The three phases (tree build, tree description, stream packing) never overlap, so
+// their scratch shares one union: 10 KiB per warp instead of 18 -- the kernel is latency-bound and shared memory was
+// what limited the warps per SM.
 struct ZkcC2Smem {
     uint32_t hist[256];
     uint32_t hist4[2][256];             // per-stream counts, two 16-bit fields per word (streams 0|1, 2|3): stream sizes without a second pass over the literals
-    uint16_t hcode[256]; uint8_t hlen[256];
-    uint8_t bitbuf[ZKC_BITBUF];
-    ZkcFse fse[1];                      // FSE table for the Huffman weights
-    uint8_t symof[512];
-    uint8_t hdr[256];                   // literal header + tree description / sequence section header + table descriptions
-    uint8_t weights[256];
+    uint16_t hcode[256]; uint8_t hlen[256];      // hcode: (length << 11) | code
+    union {
+        uint8_t bitbuf[ZKC_BITBUF];
+        struct { ZkcFse fse; uint8_t symof[512]; uint8_t weights[256]; } w;    // FSE coding of the Huffman weights
+    } u;
+    uint8_t hdr[256];                   // literal header + tree description
     uint32_t scratch[16];
 };
 
@@ -633,16 +636,16 @@ struct ZkcC2Smem {
 // in shared memory (each lane ranks 8 symbols), then lane 0 runs the two-queue tree build on shared-memory arrays
 // (aliasing the bit buffer, which is not in use yet).  Returns max code length (0 = fewer than two symbols).
 __device__ int zkc_huf_build(ZkcC2Smem& sm, int lane) {
-    uint16_t* order = (uint16_t*)sm.bitbuf;                 // 256 x u16   symbols sorted by count ascending
-    uint32_t* weight = (uint32_t*)(sm.bitbuf + 512);        // 511 x u32
-    uint16_t* parent = (uint16_t*)(sm.bitbuf + 512 + 2048); // 511 x u16
-    uint8_t* depth = sm.bitbuf + 512 + 2048 + 1024;         // 511 x u8
+    uint16_t* order = (uint16_t*)sm.u.bitbuf;                 // 256 x u16   symbols sorted by count ascending
+    uint32_t* weight = (uint32_t*)(sm.u.bitbuf + 512);        // 511 x u32
+    uint16_t* parent = (uint16_t*)(sm.u.bitbuf + 512 + 2048); // 511 x u16
+    uint8_t* depth = sm.u.bitbuf + 512 + 2048 + 1024;         // 511 x u8
     int n = 0;
     for (int s0 = 0; s0 < 256; s0 += 32) n += __popc(__ballot_sync(0xFFFFFFFFu, sm.hist[s0 + lane] != 0));
     if (n < 2) return 0;
     // compact the present symbols (ascending), then rank them among themselves: n^2 / 32 comparisons per lane instead of 256 * 8
-    uint32_t* pcnt = (uint32_t*)(sm.bitbuf + 4608);         // n x u32
-    uint8_t* psym = sm.bitbuf + 4608 + 1024;                // n x u8
+    uint32_t* pcnt = (uint32_t*)(sm.u.bitbuf + 4608);         // n x u32
+    uint8_t* psym = sm.u.bitbuf + 4608 + 1024;                // n x u8
     {
         int basep = 0;
         for (int s0 = 0; s0 < 256; s0 += 32) {
@@ -771,29 +774,29 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                     if (sm.hlen[s]) { const int w = maxlen + 1 - sm.hlen[s]; sm.hcode[s] = (uint16_t)((cls[w] >> (w - 1)) | ((uint32_t)sm.hlen[s] << 11)); cls[w] += 1u << (w - 1); }
                 // tree description: weights of symbols 0..last_sym-1 (the last one is implied)
                 int nw = last_sym;
-                for (int s = 0; s < nw; s++) sm.weights[s] = sm.hlen[s] ? (uint8_t)(maxlen + 1 - sm.hlen[s]) : 0;
+                for (int s = 0; s < nw; s++) sm.u.w.weights[s] = sm.hlen[s] ? (uint8_t)(maxlen + 1 - sm.hlen[s]) : 0;
                 uint32_t tb = 0;
                 // FSE-compressed weights (two interleaved states), A.4
                 if (nw > 1) {
                     uint32_t wc[16]; for (int i = 0; i < 16; i++) wc[i] = 0;
                     int maxw = 0;
-                    for (int s = 0; s < nw; s++) { wc[sm.weights[s]]++; if (sm.weights[s] > maxw) maxw = sm.weights[s]; }
+                    for (int s = 0; s < nw; s++) { wc[sm.u.w.weights[s]]++; if (sm.u.w.weights[s] > maxw) maxw = sm.u.w.weights[s]; }
                     uint32_t distinct = 0; for (int i = 0; i <= maxw; i++) distinct += wc[i] != 0;
                     if (distinct > 1) {
-                        ZkcFse& t = sm.fse[0];
+                        ZkcFse& t = sm.u.w.fse;
                         int lg = 6; while (lg > 5 && (1 << lg) > nw) lg--;        // table log 5..6
                         zkc_fse_normalize(t, wc, maxw + 1, (uint32_t)nw, lg);
                         t.mode = 2;
-                        zkc_fse_build(t, sm.symof);
+                        zkc_fse_build(t, sm.u.w.symof);
                         uint32_t hb = zkc_fse_write_ncount(t, sm.hdr + 1, 120);
                         if (hb) {
                             ZkcBitW w; w.init(sm.hdr + 1 + hb, 127 - hb);
                             // encode from the last weight to the first, alternating two states
                             uint32_t s1, s2; int n = nw;
-                            if (n & 1) { zkc_fse_init_state(t, sm.weights[n - 1], s1); zkc_fse_init_state(t, sm.weights[n - 2], s2); n -= 2;
-                                         zkc_fse_encode(t, w, sm.weights[n - 1], s1); n--; }
-                            else { zkc_fse_init_state(t, sm.weights[n - 1], s2); zkc_fse_init_state(t, sm.weights[n - 2], s1); n -= 2; }
-                            while (n >= 2) { zkc_fse_encode(t, w, sm.weights[n - 1], s2); zkc_fse_encode(t, w, sm.weights[n - 2], s1); n -= 2; }
+                            if (n & 1) { zkc_fse_init_state(t, sm.u.w.weights[n - 1], s1); zkc_fse_init_state(t, sm.u.w.weights[n - 2], s2); n -= 2;
+                                         zkc_fse_encode(t, w, sm.u.w.weights[n - 1], s1); n--; }
+                            else { zkc_fse_init_state(t, sm.u.w.weights[n - 1], s2); zkc_fse_init_state(t, sm.u.w.weights[n - 2], s1); n -= 2; }
+                            while (n >= 2) { zkc_fse_encode(t, w, sm.u.w.weights[n - 1], s2); zkc_fse_encode(t, w, sm.u.w.weights[n - 2], s1); n -= 2; }
                             zkc_fse_flush(t, w, s2); zkc_fse_flush(t, w, s1);
                             uint32_t sb = w.finish();
                             if (sb && hb + sb < 128 && hb + sb < (uint32_t)(nw + 1) / 2) { sm.hdr[0] = (uint8_t)(hb + sb); tb = 1 + hb + sb; }
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                 if (!tb) {
                     if (nw <= 128) {
                         sm.hdr[0] = (uint8_t)(127 + nw);
-                        for (int s = 0; s < nw; s += 2) sm.hdr[1 + s / 2] = (uint8_t)((sm.weights[s] << 4) | (s + 1 < nw ? sm.weights[s + 1] : 0));
+                        for (int s = 0; s < nw; s += 2) sm.hdr[1 + s / 2] = (uint8_t)((sm.u.w.weights[s] << 4) | (s + 1 < nw ? sm.u.w.weights[s + 1] : 0));
                         tb = 1 + (uint32_t)(nw + 1) / 2;
                     }
                 }
@@ -849,13 +852,17 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                 opos += 6;
                 // encode each stream: symbol i of the stream sits above all later symbols (the decoder reads backward),
                 // so its bit position is the sum of the code lengths of the symbols after it -> warp scan over reversed order
+                __syncwarp();                                         // the tree description has left the union
                 for (int st = 0; st < 4; st++) {
                     const uint32_t s0 = st * seg, s1 = st < 3 ? s0 + seg : nlit, m = s1 - s0;
-                    uint32_t* wbuf = (uint32_t*)sm.bitbuf;
-                    const uint32_t words = (ssz[st] + 3) / 4;
+                    uint32_t* wbuf = (uint32_t*)sm.u.bitbuf;
+                    // a stream that fits the buffer is packed there and copied out once; a longer one goes through a 48-word
+                    // window whose full words are flushed after every 128 symbols
+                    const bool whole = ssz[st] + 8 <= ZKC_BITBUF;
+                    const uint32_t words = whole ? (ssz[st] + 3) / 4 : 64u;
                     for (uint32_t i = lane; i < words; i += 32) wbuf[i] = 0;
                     __syncwarp();
-                    uint32_t base = 0;
+                    uint32_t base = 0;                                // bits of the stream emitted so far
                     for (uint32_t g = 0; g < m; g += 128) {
                         // four symbols per lane (reversed indices r .. r+3, r lowest in the stream): one scan and at most
                         // three atomics serve 128 symbols
@@ -878,20 +885,37 @@ __global__ void __launch_bounds__(32) zk_lit_enc_kernel(ZkEncodeArgs a) {
                         }
                         uint32_t incl = l;
                         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-                        const uint32_t bitpos = base + incl - l;
+                        const uint32_t org = whole ? base : (base & 31u);     // bit position of the tile inside wbuf
+                        const uint32_t bitpos = org + incl - l;
                         if (l) {
                             const uint32_t sh = bitpos & 31u, w = bitpos >> 5;
-                            const unsigned long long lo = v << sh;
-                            atomicOr(&wbuf[w], (uint32_t)lo);
-                            if (lo >> 32) atomicOr(&wbuf[w + 1], (uint32_t)(lo >> 32));
-                            if (sh) { const uint32_t hi = (uint32_t)(v >> (64u - sh)); if (hi) atomicOr(&wbuf[w + 2], hi); }
+                            const unsigned long long lo2 = v << sh;
+                            atomicOr(&wbuf[w], (uint32_t)lo2);
+                            if (lo2 >> 32) atomicOr(&wbuf[w + 1], (uint32_t)(lo2 >> 32));
+                            if (sh) { const uint32_t hi2 = (uint32_t)(v >> (64u - sh)); if (hi2) atomicOr(&wbuf[w + 2], hi2); }
                         }
-                        base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        if (!whole) {
+                            __syncwarp();
+                            const uint32_t nwords = (org + tile_bits) >> 5, byte0 = (base >> 5) * 4u;
+                            for (uint32_t i = lane; i < nwords * 4u; i += 32) out[opos + byte0 + i] = sm.u.bitbuf[i];
+                            const uint32_t carry = wbuf[nwords];
+                            __syncwarp();
+                            for (uint32_t i = lane; i <= nwords + 2; i += 32) wbuf[i] = i == 0 ? carry : 0u;
+                            __syncwarp();
+                        }
+                        base += tile_bits;
                     }
                     __syncwarp();
-                    if (lane == 0) atomicOr(&wbuf[base >> 5], 1u << (base & 31));   // end mark
-                    __syncwarp();
-                    for (uint32_t i = lane; i < ssz[st]; i += 32) out[opos + i] = sm.bitbuf[i];
+                    if (whole) {
+                        if (lane == 0) atomicOr(&wbuf[base >> 5], 1u << (base & 31));   // end mark
+                        __syncwarp();
+                        for (uint32_t i = lane; i < ssz[st]; i += 32) out[opos + i] = sm.u.bitbuf[i];
+                    } else if (lane == 0) {
+                        const unsigned long long tail = (unsigned long long)wbuf[0] | (1ull << (base & 31u));
+                        const uint32_t byte0 = (base >> 5) * 4u;
+                        for (uint32_t i = 0; byte0 + i < ssz[st]; i++) out[opos + byte0 + i] = (uint8_t)(tail >> (8u * i));
+                    }
                     opos += ssz[st];
                     __syncwarp();
                 }
