@@ -6,9 +6,9 @@
 // seekable format, seekable_format.md:23-29):
 //
 //   K-D0 zk_scan_kernel     one thread / entry : walk frame + block headers, carve scratch
-//   K-D1s zk_seq_kernel     one LANE  / block  : FSE sequence decode (tables + state machine in smem)
-//   K-D1h zk_huf_kernel     one LANE  / stream : Huffman literal decode (4 lanes per 4-stream block)
-//   K-D2 zk_exec_kernel     one CTA   / entry  : ordered sequence execution through a shared-memory window
+//   K-D1s zk_seq_kernel     one LANE  / block  : FSE sequence decode (4-byte cells + state machine in smem)
+//   K-D1h zk_huf_kernel     one LANE  / stream : Huffman literal decode (4 lanes per 4-stream block, two-level table)
+//   K-D2 zk_exec_kernel[_w5] one CTA  / entry  : ordered sequence execution through a shared-memory window
 //   K-D3 zk_xxh64_kernel    one warp  / entry  : content checksum (only if requested & present)
 //
 // Format rules: RFC 8878 as restated in SURVEY.md Appendix A (the arithmetic is not in the

@@ -6,11 +6,12 @@
 // with kernels over a whole batch of independent frames (seekable_format.md:23-29); every frame is cut
 // into zstd blocks of ZKC_BLOCK bytes and every block is one unit of work:
 //
-//   K-C1 zk_match_kernel     one warp / block : LZ77 match finding (hash table in shared memory),
-//                                               greedy parse resolved with ballots, sequence + literal emit
-//   K-C2s zk_seq_enc_kernel  one LANE / block : FSE sequences (repeat offsets, normalise, table build, backward bitstream)
-//   K-C2l zk_lit_enc_kernel  one warp / block : Huffman literals (4 streams, warp-scan bit packing) + block assembly
-//   K-C3 zk_frame_layout_kernel / zk_frame_gather_kernel : frame headers, block gather, optional XXH64
+//   K-C1 zk_match_kernel<HLOG> one warp / block : LZ77 match finding (hash table in shared memory), greedy parse resolved
+//                                               with ballots, repeat-offset codes, sequences + literals written per window
+//   K-C2s zk_seq_enc_kernel  one warp / block : FSE sequences (three lanes run the state chains, 32 lanes pack the bits)
+//   K-C2l zk_lit_enc_kernel  one warp / block : Huffman literals (tree build, FSE-coded weights, 4 streams packed by warp scan)
+//   K-C2f zk_block_finish_kernel              : joins the two sections of a block (coded on two streams), Raw fallback, header
+//   K-C3 zk_frame_{hash,size,scan,gather}_kernel : optional XXH64, frame sizes, offsets, frame headers + block gather
 //
 // Output is a standard Zstandard frame per seek-table entry (RFC 8878), decodable
 // by libzstd; the compressed bytes are NOT meant to equal libzstd's.
@@ -18,7 +19,7 @@
 #include <string.h>
 
 #define ZKC_BLOCK 32768u                 // zstd block size used by this encoder (<= Block_Maximum_Size)
-#define ZKC_HLOG_FAST 11                 // hash table per warp: 2048 x u16 at level 1 (36 warps / SM hide the two dependent loads per window),
+#define ZKC_HLOG_FAST 11                 // hash table per warp: 2048 x u16 at level 1 (40 warps / SM hide the two dependent loads per window),
 #define ZKC_HLOG 12                      // 4096 x u16 from level 2 on (24 warps / SM, 0.3-3 % better ratio)
 #define ZKC_MINMATCH 5
 #define ZKC_MAXSEQ (ZKC_BLOCK / 4 + 8)   // every sequence covers at least 4 bytes (repeat matches may be 4 long); multiple of 8 for 16-byte chunked loads
