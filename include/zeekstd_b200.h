@@ -96,6 +96,13 @@ int32_t zk_compress_frames(zk_ctx* ctx, const uint8_t* src, size_t n, uint32_t f
 int32_t zk_decompress_frames(zk_ctx* ctx, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
                              uint32_t n_frames, uint8_t* dst, int32_t verify_checksum, int32_t* status);
 
+/* Range reads (decode.rs:228-266 decodes a frame only as far as offset_limit): like
+ * zk_decompress_frames, but entry i is only guaranteed to hold its first d_need[i] bytes afterwards (the decoder stops at
+ * the first block boundary at or after that point; the rest of the entry's output range is unspecified).  A prefix is
+ * not checksum-verified, as in the reference (decode.rs:425-427).  d_need == NULL or d_need[i] >= the entry's size: everything. */
+int32_t zk_decompress_frames_upto(zk_ctx* ctx, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
+                                  uint32_t n_frames, uint8_t* dst, const uint32_t* d_need, int32_t verify_checksum, int32_t* status);
+
 /*
  * Device-resident variants (zero-copy; used for roofline measurements and multi-GPU pipelines).
  * d_* are CUDA device pointers, 16-byte aligned, with >= 16 readable bytes after the last byte;

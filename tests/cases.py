@@ -10,6 +10,7 @@ import numpy as np
 
 import zeekstd_b200 as zk
 from oracle import oracle as O
+from zeekstd_b200 import _native, corpus
 from util import decode_frames, golden_bytes, golden_meta, offsets, split_frames
 
 INPUT = golden_bytes("dickens_96k.txt")[:12_345]       # plays the role of lib.rs's INPUT (the reference uses its own source text)
@@ -367,6 +368,41 @@ def check_libzstd_archive_through_decoder(ctx):
         dec.set_offset(lo); dec.set_offset_limit(hi)
         assert dec.read_all() == data[lo:hi].tobytes()
         dec.set_offset_limit(data.size)
+
+
+def check_range_reads_stop_early(ctx, n: int = 600_000, frame_size: int = 300_000, reads: int = 24):
+    """a range read decodes its last frame only as far as offset_limit (block granularity).  Multi-block
+    frames (libzstd: 128 KiB blocks; ours: 32 KiB), checksum on: the prefix must be exact, growing the limit afterwards
+    must still give the right bytes, and zk_decompress_frames_upto must leave at least the wanted prefix of every entry"""
+    data = np.concatenate([corpus.make_class("text", n // 2, 11).numpy(), corpus.make_class("structured", n - n // 2, 12).numpy()])
+    rng = np.random.default_rng(17)
+    for archive in (O.ref_seekable_archive(data, frame_size, 1, True)[0], None):
+        if archive is None:
+            sink = io.BytesIO()
+            enc = zk.EncodeOptions(ctx).checksum_flag(True).frame_size_policy(zk.FrameSizePolicy.Uncompressed(frame_size)).into_encoder(sink)
+            enc.write(data.tobytes()); enc.finish(); archive = sink.getvalue()
+        dec = zk.Decoder(zk.DecodeOptions(archive, ctx))
+        for _ in range(reads):
+            lo = int(rng.integers(0, data.size - 1)); hi = int(rng.integers(lo + 1, min(data.size, lo + 70_000) + 1))
+            dec.set_offset(lo); dec.set_offset_limit(hi)
+            assert dec.read_all() == data[lo:hi].tobytes()
+            if rng.integers(2):                                  # continue past the old limit inside the same frame
+                hi2 = min(data.size, hi + int(rng.integers(1, 200_000)))
+                dec.set_offset_limit(hi2)
+                assert dec.read_all() == data[hi:hi2].tobytes()
+            dec.set_offset_limit(data.size)
+    # the batch entry point directly
+    frames, cs, ds = O.ref_compress_frames(data, frame_size, 1, True)
+    comp = np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8)
+    co = np.zeros(len(cs) + 1, dtype=np.uint64); co[1:] = np.cumsum(cs)
+    do = np.zeros(len(ds) + 1, dtype=np.uint64); do[1:] = np.cumsum(ds)
+    need = np.array([int(rng.integers(0, d + 1)) for d in ds], dtype=np.uint32)
+    out = np.zeros(int(do[-1]) + 64, dtype=np.uint8); st = np.zeros(len(cs), dtype=np.int32)
+    rc = ctx.lib.zk_decompress_frames_upto(ctx._h, comp.ctypes.data, co.ctypes.data_as(_native.u64p), do.ctypes.data_as(_native.u64p), len(cs),
+                                           out.ctypes.data, need.ctypes.data_as(_native.u32p), 1, st.ctypes.data_as(_native.i32p))
+    assert rc == 0 and not st.any()
+    for i, d in enumerate(ds):
+        a0 = int(do[i]); assert out[a0:a0 + int(need[i])].tobytes() == data[a0:a0 + int(need[i])].tobytes()
 
 
 # ------------------------------------------------------------------------------------------------ seek table (host only)

@@ -111,6 +111,12 @@ def test_api_decode_side(ctx):
     cases.check_libzstd_archive_through_decoder(ctx)
 
 
+@pytest.mark.gpu
+def test_range_reads_stop_early(ctx):
+    cases.check_range_reads_stop_early(ctx, n=9_000_000, frame_size=2 << 20, reads=40)
+
+
+
 def test_seek_table(gpu_lib):
     cases.check_seek_table(gpu_lib)
 

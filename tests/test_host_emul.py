@@ -115,3 +115,8 @@ def test_decoder_state_machine(ctx):
 
 def test_libzstd_archive_through_decoder(ctx):
     cases.check_libzstd_archive_through_decoder(ctx)
+
+
+
+def test_range_reads_stop_early(ctx):
+    cases.check_range_reads_stop_early(ctx)

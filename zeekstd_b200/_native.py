@@ -52,6 +52,7 @@ _SIGS = {
     "zk_compress_frames": (c_int32, [c_void_p, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_void_p, c_size_t,
                                      u32p, u32p, c_uint32, u32p, POINTER(c_size_t)]),
     "zk_decompress_frames": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, c_int32, i32p]),
+    "zk_decompress_frames_upto": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, u32p, c_int32, i32p]),
     "zk_compress_frames_dev": (c_int32, [c_void_p, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_void_p, c_size_t,
                                          u32p, u32p, c_uint32, u32p, POINTER(c_size_t), c_void_p]),
     "zk_decompress_frames_dev": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, c_int32, i32p,

@@ -213,7 +213,7 @@ struct ZkTrace {
 struct ZkSubDec { uint32_t first = 0, count = 0; std::vector<uint64_t> c_rel, d_rel; bool busy = false; };
 
 static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
-                              uint8_t* dst, int verify, ZkTrace* tr = nullptr, int k = 0) {
+                              uint8_t* dst, int verify, ZkTrace* tr = nullptr, int k = 0, const uint32_t* need = nullptr) {
     ZkSlot& s = c->slot[si];
     uint32_t f = sb.first, cnt = sb.count;
     size_t cbytes = (size_t)(c_off[f + cnt] - c_off[f]), obytes = (size_t)(d_off[f + cnt] - d_off[f]);
@@ -226,6 +226,7 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     if (tr) tr->mark(s.stream, k, 1);
     s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
     s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", 3);
+    s.dws.need = need ? need + f : nullptr;
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
     if (rc) return rc;
@@ -237,12 +238,12 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
 }
 
 static int zk_dec_sub_finish(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
-                             uint8_t* dst, int verify, int32_t* status) {
+                             uint8_t* dst, int verify, int32_t* status, const uint32_t* need = nullptr) {
     ZkSlot& s = c->slot[si];
     if (!sb.busy) return 0;
     int rc = zk_decode_collect(&s.dws, s.stream, status ? status + sb.first : nullptr);
     if (rc == ZK_ST_RETRY) {            // scratch was too small for this sub-batch: exact needs are known now
-        rc = zk_dec_sub_enqueue(c, si, sb, comp, c_off, d_off, dst, verify);
+        rc = zk_dec_sub_enqueue(c, si, sb, comp, c_off, d_off, dst, verify, nullptr, 0, need);
         if (rc) { sb.busy = false; return rc; }
         rc = zk_decode_collect(&s.dws, s.stream, status ? status + sb.first : nullptr);
         if (rc == ZK_ST_RETRY) rc = ZK_ERR_ZSTD(ZKZ_MEMORY_ALLOCATION);
@@ -253,6 +254,11 @@ static int zk_dec_sub_finish(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* com
 
 extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
                                         uint32_t n, uint8_t* dst, int32_t verify, int32_t* status) {
+    return zk_decompress_frames_upto(c, comp, c_off, d_off, n, dst, nullptr, verify, status);
+}
+
+extern "C" int32_t zk_decompress_frames_upto(zk_ctx* c, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
+                                             uint32_t n, uint8_t* dst, const uint32_t* d_need, int32_t verify, int32_t* status) {
     if (!c || (n && (!comp || !c_off || !d_off || !dst))) return ZK_ERR_INVALID_ARG;
     if (n == 0) return 0;
     ZK_RT_OK(cudaSetDevice(c->device));
@@ -264,16 +270,16 @@ extern "C" int32_t zk_decompress_frames(zk_ctx* c, const uint8_t* comp, const ui
     ZkTrace tr; tr.begin(c->slot[0].stream);
     for (uint32_t first = 0; first < n; k++) {
         int si = (int)(k % NS);
-        int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
+        int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status, d_need);
         if (rc && !worst) worst = rc;
         uint32_t end = zk_next_sub(d_off, first, n, sub_bytes, 1u << 20);
         sub[si].first = first; sub[si].count = end - first;
-        rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify, &tr, (int)k);
+        rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify, &tr, (int)k, d_need);
         if (rc) { if (!worst) worst = rc; break; }
         first = end;
     }
     for (int si = 0; si < ZK_SLOTS; si++) {
-        int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status);
+        int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status, d_need);
         if (rc && !worst) worst = rc;
     }
     tr.end("dec");

@@ -906,8 +906,12 @@ __device__ __forceinline__ void zk_exec_body(ZkD2Smem& sm, const ZkDecodeArgs& a
     uint32_t pos = 0, zstart = 0, chunk_base = 0;
     uint32_t R0 = 1, R1 = 4, R2 = 8;
     uint32_t preannounced = 0xFFFFFFFFu;          // chunk id this warp has already announced ahead of time
+    // range reads: stop at the first block boundary at or after the wanted prefix (every warp takes the same decision)
+    const uint32_t need = a.d_need ? a.d_need[e] : 0xFFFFFFFFu;
+    bool stopped = false;
     for (uint32_t bi = 0; bi < ent.n_blocks; bi++) {
         if (zk_d2_aborted(sm)) break;
+        if (pos >= need) { stopped = true; break; }
         const uint32_t bidx = ent.first_block + bi;
         const ZkBlock blk = a.blocks[bidx];
         if (blk.flags & ZKB_FIRST) { R0 = 1; R1 = 4; R2 = 8; zstart = pos; }
@@ -1209,7 +1213,7 @@ __device__ __forceinline__ void zk_exec_body(ZkD2Smem& sm, const ZkDecodeArgs& a
     __syncthreads();
     if (threadIdx.x == 0) {
         int code = sm.abort_code;
-        if (!code && (unsigned long long)pos != cap64) code = pos < cap64 ? ZKZ_SRC_SIZE_WRONG : ZKZ_DST_TOO_SMALL;
+        if (!code && !stopped && (unsigned long long)pos != cap64) code = pos < cap64 ? ZKZ_SRC_SIZE_WRONG : ZKZ_DST_TOO_SMALL;
         a.entries[e].status = code ? -code : 0;
         a.entries[e].produced = pos;
         if (code) atomicAdd(&a.counters->n_errors, 1u);
@@ -1285,6 +1289,7 @@ __global__ void __launch_bounds__(128) zk_xxh64_kernel(ZkDecodeArgs a) {
     if (e >= a.n_entries) return;
     ZkEntry ent = a.entries[e];
     if (ent.status != 0 || a.counters->overflow) return;
+    if (a.d_need && (unsigned long long)a.d_need[e] < a.d_off[e + 1] - a.d_off[e]) return;   // a prefix only: no checksum, as the reference (decode.rs:425-427)
     const uint8_t* out = a.dst + a.d_off[e];
     const uint8_t* ebase = a.comp + a.c_off[e];
     for (uint32_t bi = 0; bi < ent.n_blocks; bi++) {
@@ -1322,8 +1327,9 @@ static int zk_grow(void** p, size_t* cap, size_t need, size_t elem) {
 
 void zk_decode_ws_free(ZkDecodeWs* ws) {
     void* ptrs[] = { ws->blocks, ws->entries, ws->counters, ws->lit, ws->seq_lit_end, ws->seq_out_end, ws->seq_off, ws->c_off, ws->d_off,
-                     ws->huf_list, ws->seq_list };
+                     ws->huf_list, ws->seq_list, ws->d_need };
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (ws->h_need) cudaFreeHost(ws->h_need);
     if (ws->h_entries) cudaFreeHost(ws->h_entries);
     if (ws->h_counters) cudaFreeHost(ws->h_counters);
     if (ws->h_off) cudaFreeHost(ws->h_off);
@@ -1364,6 +1370,10 @@ static int zk_decode_ensure(ZkDecodeWs* ws, uint32_t n, size_t need_blocks, size
         if (ws->h_off) cudaFreeHost(ws->h_off);
         if (cudaMallocHost((void**)&ws->h_entries, c * sizeof(ZkEntry)) != cudaSuccess) return -(int)ZKZ_MEMORY_ALLOCATION;
         if (cudaMallocHost((void**)&ws->h_off, 2 * (c + 1) * 8) != cudaSuccess) return -(int)ZKZ_MEMORY_ALLOCATION;
+        if (ws->d_need) { cudaFree(ws->d_need); ws->d_need = nullptr; }
+        if (ws->h_need) { cudaFreeHost(ws->h_need); ws->h_need = nullptr; }
+        if (cudaMalloc((void**)&ws->d_need, (c + 1) * 4) != cudaSuccess) return -(int)ZKZ_MEMORY_ALLOCATION;
+        if (cudaMallocHost((void**)&ws->h_need, (c + 1) * 4) != cudaSuccess) return -(int)ZKZ_MEMORY_ALLOCATION;
         ws->cap_entries = c;
     }
     if (!ws->counters) {
@@ -1402,6 +1412,12 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     a.huf_list = ws->huf_list; a.seq_list = ws->seq_list;
     a.cap_blocks = ws->cap_blocks; a.cap_lit = ws->cap_lit - 64; a.cap_seq = ws->cap_seq;
     a.trace = nullptr;
+    a.d_need = nullptr;
+    if (ws->need) {
+        memcpy(ws->h_need, ws->need, (size_t)n * 4);
+        ZK_CUDA_OK(cudaMemcpyAsync(ws->d_need, ws->h_need, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+        a.d_need = ws->d_need; ws->need = nullptr;
+    }
 #ifndef ZK_EMUL
     if (getenv("ZK_EXEC_TRACE")) {
         if (!ws->trace) cudaMalloc((void**)&ws->trace, 1024 * 8 * 8);

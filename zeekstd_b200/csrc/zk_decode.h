@@ -14,6 +14,7 @@ struct ZkDecodeArgs {                 // kernel parameter block (by value)
     uint32_t* huf_list; uint32_t* seq_list;   // compacted indices of blocks with Huffman literals / with sequences
     unsigned long long cap_blocks, cap_lit, cap_seq;
     unsigned long long* trace;        // debug: per-chunk clock64 stamps of entry 0 (env ZK_EXEC_TRACE), else nullptr
+    const uint32_t* d_need;           // per entry: only this many leading bytes are wanted (range reads); nullptr = everything
 };
 
 struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on demand, reused across batches
@@ -23,6 +24,8 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint8_t* lit = nullptr; size_t cap_lit = 0;
     uint32_t* seq_lit_end = nullptr; uint32_t* seq_out_end = nullptr; uint32_t* seq_off = nullptr; size_t cap_seq = 0;
     uint64_t* c_off = nullptr; uint64_t* d_off = nullptr;
+    const uint32_t* need = nullptr;   // host array for the NEXT enqueue (one-shot): leading bytes wanted per entry, see ZkDecodeArgs::d_need
+    uint32_t* d_need = nullptr; uint32_t* h_need = nullptr;
     uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
     bool attr_set = false; uint32_t ring_override = 0;
     uint32_t huf_pad = 0;             // extra dynamic smem per Huffman CTA: fewer resident CTAs -> more L1 for the streams (tuning)

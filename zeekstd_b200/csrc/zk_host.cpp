@@ -517,13 +517,15 @@ struct zk_decoder {                        // decode.rs:121-466
     // decoded window: frames [win_lo, win_hi) live in `window` (whole frames; forward seeks inside it cost nothing,
     // mirroring "no reset when seeking forward in the same frame", decode.rs:407-410)
     uint32_t win_lo = 0, win_hi = 0; std::vector<uint8_t> window; std::vector<uint8_t> comp;
+    uint64_t win_valid_end = 0;            // the window is decoded up to this decompressed offset (< d[win_hi] after a range read)
     size_t max_window_bytes = (size_t)256 << 20;
 
-    void reset_dctx() { read_compressed = 0; win_lo = win_hi = 0; window.clear(); }                           // :352-357
+    void reset_dctx() { read_compressed = 0; win_lo = win_hi = 0; win_valid_end = 0; window.clear(); }                           // :352-357
     int32_t check_offset(uint64_t off) const { return off > seek_table.d.back() ? ZK_ERR_OFFSET_OUT_OF_RANGE : 0; }   // :439-445
 
-    // make frames [f0, f1) resident
-    int32_t load(uint32_t f0, uint32_t f1) {
+    // make frames [f0, f1) resident; need_end < d[f1]: the last frame only as far as need_end (a range read stops at
+    // offset_limit, decode.rs:228-266 -- the codec then stops at the next block boundary)
+    int32_t load(uint32_t f0, uint32_t f1, uint64_t need_end) {
         const uint64_t c0 = seek_table.c[f0], c1 = seek_table.c[f1], d0 = seek_table.d[f0], d1 = seek_table.d[f1];
         comp.resize((size_t)(c1 - c0) + 64);
         int32_t rc = src.set_offset(0, (int64_t)c0);
@@ -540,9 +542,14 @@ struct zk_decoder {                        // decode.rs:121-466
         const uint32_t n = f1 - f0;
         std::vector<uint64_t> co(n + 1), dof(n + 1);
         for (uint32_t i = 0; i <= n; i++) { co[i] = seek_table.c[f0 + i] - c0; dof[i] = seek_table.d[f0 + i] - d0; }
-        rc = zk_decompress_frames(ctx, comp.data(), co.data(), dof.data(), n, window.data(), 1, nullptr);
-        if (rc) { win_lo = win_hi = 0; return rc; }
-        win_lo = f0; win_hi = f1;
+        std::vector<uint32_t> need;
+        if (need_end < d1 && need_end > seek_table.d[f1 - 1]) {
+            need.assign(n, 0xFFFFFFFFu);
+            need[n - 1] = (uint32_t)(need_end - seek_table.d[f1 - 1]);
+        } else need_end = d1;
+        rc = zk_decompress_frames_upto(ctx, comp.data(), co.data(), dof.data(), n, window.data(), need.empty() ? nullptr : need.data(), 1, nullptr);
+        if (rc) { win_lo = win_hi = 0; win_valid_end = 0; return rc; }
+        win_lo = f0; win_hi = f1; win_valid_end = need_end;
         return 0;
     }
 };
@@ -581,17 +588,17 @@ extern "C" int32_t zk_decoder_decompress(zk_decoder* d, uint8_t* buf, size_t len
     const uint32_t nframes = d->seek_table.num_frames();
     while (d->offset < d->offset_limit && progress < len && nframes) {
         const uint32_t f = d->seek_table.index_at(d->offset, d->seek_table.d);
-        if (!(f >= d->win_lo && f < d->win_hi)) {
+        if (!(f >= d->win_lo && f < d->win_hi) || d->offset >= d->win_valid_end) {
             // decode the frames covering the rest of this request in one batch (bounded)
             const uint64_t want_end = std::min<uint64_t>(d->offset_limit, d->offset + (len - progress));
             uint32_t f1 = d->seek_table.index_at(want_end ? want_end - 1 : 0, d->seek_table.d) + 1;
             if (f1 <= f) f1 = f + 1;
             while (f1 > f + 1 && d->seek_table.d[f1] - d->seek_table.d[f] > d->max_window_bytes) f1--;
-            int32_t rc = d->load(f, f1);
+            int32_t rc = d->load(f, f1, d->offset_limit);
             if (rc) { if (produced) *produced = progress; return rc; }
         }
         const uint64_t w0 = d->seek_table.d[d->win_lo], w1 = d->seek_table.d[d->win_hi];
-        const uint64_t end = std::min<uint64_t>(std::min<uint64_t>(d->offset_limit, w1), d->offset + (len - progress));
+        const uint64_t end = std::min<uint64_t>(std::min<uint64_t>(d->offset_limit, std::min<uint64_t>(w1, d->win_valid_end)), d->offset + (len - progress));
         if (end <= d->offset) break;                                   // empty frames only
         const size_t n = (size_t)(end - d->offset);
         memcpy(buf + progress, d->window.data() + (size_t)(d->offset - w0), n);
