@@ -13,7 +13,10 @@ N > 1: every rank owns one GPU and its own shard of frames (frames are independe
 the only exchange is an all-gather of the per-frame sizes that make up the global seek table ("scaling": "weak").
 
 --impl reference times the reference's own CPU path: libzstd driven through zeekstd's call sequence
-(oracle/libzstd_driver.c; the Rust crate itself cannot be built in this image -- no cargo, no network).
+(oracle/libzstd_driver.c; the Rust crate itself cannot be built in this image -- no cargo, no network), the frames of
+the same workload spread over every host thread; what one thread reaches (zeekstd itself is single-threaded) is
+reported beside it as `single_thread`.  `roofline.traffic` comes from the committed ncu capture of this workload
+(profiles/traffic_r1.json): a bench value is never taken under a profiler.
 """
 from __future__ import annotations
 
