@@ -130,8 +130,10 @@ class Context:
                                       byref(dl)), lib)
         return dst[: dl.value], cs[: nf.value].copy(), ds[: nf.value].copy()
 
-    def decompress_frames(self, comp, c_off, d_off, verify_checksum: bool = True, out: np.ndarray | None = None):
-        """decode frames given N+1 cumulative offsets -> (np.uint8 output, per-frame status)"""
+    def decompress_frames(self, comp, c_off, d_off, verify_checksum: bool = True, out: np.ndarray | None = None, need=None):
+        """decode frames given N+1 cumulative offsets -> (np.uint8 output, per-frame status, rc).
+        need (optional, one uint32 per frame): only that many leading bytes of each frame are wanted (range reads,
+        zk_decompress_frames_upto): the rest of a frame's output range is then unspecified and its checksum is not verified."""
         addr, n, keep = _buf(comp)
         co = np.ascontiguousarray(c_off, dtype=np.uint64); do = np.ascontiguousarray(d_off, dtype=np.uint64)
         nf = len(co) - 1
@@ -139,8 +141,12 @@ class Context:
         if out is None:
             out = np.empty(total + 64, dtype=np.uint8)
         st = np.zeros(max(nf, 1), dtype=np.int32)
-        rc = self.lib.zk_decompress_frames(self._h, addr, co.ctypes.data_as(_native.u64p), do.ctypes.data_as(_native.u64p), nf,
-                                           out.ctypes.data, int(verify_checksum), st.ctypes.data_as(_native.i32p))
+        nd = None if need is None else np.ascontiguousarray(need, dtype=np.uint32)
+        if nd is not None and len(nd) != nf:
+            raise ValueError("need: one entry per frame")
+        rc = self.lib.zk_decompress_frames_upto(self._h, addr, co.ctypes.data_as(_native.u64p), do.ctypes.data_as(_native.u64p), nf,
+                                                out.ctypes.data, None if nd is None else nd.ctypes.data_as(_native.u32p),
+                                                int(verify_checksum), st.ctypes.data_as(_native.i32p))
         return out[:total], st[:nf], rc
 
 
