@@ -53,6 +53,23 @@ def test_sharded_roundtrip_world2(n_total, frame_size, expect_frames):
     assert ds == [min(frame_size, n_total - i * frame_size) for i in range(expect_frames)] if n_total else ds == [0]
 
 
+def test_sharded_roundtrip_world3_with_idle_rank():
+    """2 frames over 3 ranks: the last rank owns no frame and must still take part in every exchange"""
+    from zeekstd_b200.build import build_emul
+    build_emul()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctxm.Process(target=_worker, args=(r, 3, port, 15_000, 10_000, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    ok, nf, ds = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok and nf == 2 and ds == [10_000, 5_000]
+
+
 def test_frame_ranges():
     from zeekstd_b200.parallel import frame_ranges
     assert frame_ranges(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
