@@ -265,6 +265,7 @@ extern "C" int32_t zk_decompress_frames_upto(zk_ctx* c, const uint8_t* comp, con
     const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);     // measured best on B200 (tools/e2e_sweep2.sh)
     ZkSubDec sub[ZK_SLOTS];
     const int NS = zk_host_slots(false);
+    const bool ramp = zk_env_size("ZK_HOST_RAMP", 0) != 0;
     int32_t worst = 0;
     uint32_t k = 0;
     ZkTrace tr; tr.begin(c->slot[0].stream);
@@ -272,7 +273,9 @@ extern "C" int32_t zk_decompress_frames_upto(zk_ctx* c, const uint8_t* comp, con
         int si = (int)(k % NS);
         int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status, d_need);
         if (rc && !worst) worst = rc;
-        uint32_t end = zk_next_sub(d_off, first, n, sub_bytes, 1u << 20);
+        // ZK_HOST_RAMP=1 (experimental, off): quarter- and half-size first sub-batches, so that the first D2H starts earlier
+        const size_t this_sub = ramp && k < 2 ? sub_bytes >> (2 - k) : sub_bytes;
+        uint32_t end = zk_next_sub(d_off, first, n, this_sub, 1u << 20);
         sub[si].first = first; sub[si].count = end - first;
         rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify, &tr, (int)k, d_need);
         if (rc) { if (!worst) worst = rc; break; }
