@@ -15,6 +15,12 @@
  *              lib/src/encode.rs:599      staging buffer = ZSTD_CStreamOutSize()
  *   decompress lib/src/decode.rs:221-256  decompress_stream with DStreamInSize /
  *              DStreamOutSize staging buffers (decode.rs:181-184)
+ *   prefix     lib/src/encode.rs:332-338  cctx.ref_prefix(pref) when frame_d_size == 0 (start of every frame)
+ *              lib/src/decode.rs:211-214  dctx.ref_prefix(pref) before the first frame,
+ *              lib/src/decode.rs:246-255  reset(SessionOnly) + ref_prefix(pref) after every frame end (n == 0)
+ *
+ * plus ZSTD_compress() one-shot frames (Single_Segment / Frame_Content_Size headers: what other
+ * libzstd producers emit and the Decoder must accept) for the coverage fixtures.
  *
  * so it is (a) the oracle every parity test compares against ("bit-exact vs
  * the reference Decoder" == equality with ZSTD_decompressStream output) and
@@ -51,6 +57,9 @@ static struct {
     int (*getErrorCode)(size_t);
     const char* (*versionString)(void);
     size_t (*compressBound)(size_t);
+    size_t (*compress)(void*, size_t, const void*, size_t, int);
+    size_t (*CCtx_refPrefix)(void*, const void*, size_t);
+    size_t (*DCtx_refPrefix)(void*, const void*, size_t);
 } Z;
 
 #define ZSTD_c_compressionLevel 100
@@ -74,6 +83,7 @@ int zkr_open(const char* path) {
     LOAD(DStreamOutSize, "ZSTD_DStreamOutSize"); LOAD(isError, "ZSTD_isError");
     LOAD(getErrorCode, "ZSTD_getErrorCode"); LOAD(versionString, "ZSTD_versionString");
     LOAD(compressBound, "ZSTD_compressBound");
+    LOAD(compress, "ZSTD_compress"); LOAD(CCtx_refPrefix, "ZSTD_CCtx_refPrefix"); LOAD(DCtx_refPrefix, "ZSTD_DCtx_refPrefix");
     return 0;
 }
 const char* zkr_version(void) { return Z.h ? Z.versionString() : "unloaded"; }
@@ -82,9 +92,13 @@ size_t zkr_compress_bound(size_t n) { return Z.compressBound(n); }
 /* Compress ONE frame the way RawEncoder does (encode.rs:311-354 + 438-472).
  * Returns compressed size or -(libzstd error code). */
 static int64_t compress_one_frame(void* cctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap,
-                                  uint8_t* stage, size_t stage_sz) {
+                                  uint8_t* stage, size_t stage_sz, const uint8_t* prefix, size_t prefix_len) {
     ZSTD_inBuffer in = { src, n, 0 };
     size_t written = 0;
+    if (prefix && n) {                         /* encode.rs:332-338: only once input arrives (frame_d_size == 0 at the first compress call) */
+        size_t r = Z.CCtx_refPrefix(cctx, prefix, prefix_len);
+        if (Z.isError(r)) return -(int64_t)Z.getErrorCode(r);
+    }
     while (in.pos < n) {                       /* Encoder::compress_with_prefix loop, encode.rs:648-661 */
         ZSTD_outBuffer out = { stage, stage_sz, 0 };
         while (in.pos < n && out.pos < out.size) {   /* encode.rs:340-346 */
@@ -109,9 +123,13 @@ static int64_t compress_one_frame(void* cctx, const uint8_t* src, size_t n, uint
 
 /* Decompress ONE seek-table entry's bytes as Decoder::decompress does (decode.rs:221-256). */
 static int64_t decompress_one_frame(void* dctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap,
-                                    size_t in_chunk, size_t out_chunk) {
+                                    size_t in_chunk, size_t out_chunk, const uint8_t* prefix, size_t prefix_len) {
     size_t ipos = 0, opos = 0;
     size_t last = 1;
+    if (prefix) {                               /* decode.rs:211-214 */
+        size_t r = Z.DCtx_refPrefix(dctx, prefix, prefix_len);
+        if (Z.isError(r)) return -(int64_t)Z.getErrorCode(r);
+    }
     while (ipos < n) {
         size_t take = n - ipos < in_chunk ? n - ipos : in_chunk;    /* src.read(&mut in_buf), decode.rs:222-225 */
         ZSTD_inBuffer in = { src + ipos, take, 0 };
@@ -122,6 +140,12 @@ static int64_t decompress_one_frame(void* dctx, const uint8_t* src, size_t n, ui
             last = Z.decompressStream(dctx, &out, &in);             /* decode.rs:243-245 */
             if (Z.isError(last)) { Z.DCtx_reset(dctx, ZSTD_reset_session_only); return -(int64_t)Z.getErrorCode(last); }
             opos += out.pos;
+            if (last == 0 && prefix) {                              /* frame end: decode.rs:246-255 */
+                Z.DCtx_reset(dctx, ZSTD_reset_session_only);
+                size_t r = Z.DCtx_refPrefix(dctx, prefix, prefix_len);
+                if (Z.isError(r)) return -(int64_t)Z.getErrorCode(r);
+                continue;
+            }
             if (out.pos == 0 && in.pos == before) {                 /* no progress: output exhausted */
                 Z.DCtx_reset(dctx, ZSTD_reset_session_only); return room == 0 ? -70 : -72;
             }
@@ -148,6 +172,7 @@ typedef struct {
     uint8_t* dst; size_t slot;            /* compress: per-frame output slots of `slot` bytes */
     const uint64_t* c_off; const uint64_t* d_off; size_t dst_cap;   /* decompress */
     uint32_t n_frames; int64_t* sizes; int64_t err;
+    const uint8_t* prefix; size_t prefix_len;
 } job;
 
 static void* compress_worker(void* arg) {
@@ -163,7 +188,7 @@ static void* compress_worker(void* arg) {
     for (uint32_t f = lo; f < hi; f++) {
         size_t off = (size_t)f * j->frame_size;
         size_t len = j->n - off < j->frame_size ? j->n - off : j->frame_size;
-        int64_t r = compress_one_frame(cctx, j->src + off, len, j->dst + (size_t)f * j->slot, j->slot, stage, stage_sz);
+        int64_t r = compress_one_frame(cctx, j->src + off, len, j->dst + (size_t)f * j->slot, j->slot, stage, stage_sz, j->prefix, j->prefix_len);
         j->sizes[f] = r;
         if (r < 0) { j->err = r; break; }
     }
@@ -179,7 +204,7 @@ static void* decompress_worker(void* arg) {
     uint32_t lo = per * j->tid, hi = lo + per > j->n_frames ? j->n_frames : lo + per;
     for (uint32_t f = lo; f < hi; f++) {
         int64_t r = decompress_one_frame(dctx, j->src + j->c_off[f], (size_t)(j->c_off[f + 1] - j->c_off[f]),
-                                         j->dst + j->d_off[f], (size_t)(j->d_off[f + 1] - j->d_off[f]), in_chunk, out_chunk);
+                                         j->dst + j->d_off[f], (size_t)(j->d_off[f + 1] - j->d_off[f]), in_chunk, out_chunk, j->prefix, j->prefix_len);
         j->sizes[f] = r;
         if (r < 0 && !j->err) j->err = r;
     }
@@ -228,7 +253,33 @@ int64_t zkr_decompress_frames(const uint8_t* comp, const uint64_t* c_off, const 
 /* Decompress an arbitrary buffer of concatenated frames into dst (cap bytes); returns size or -(code). */
 int64_t zkr_decompress_any(const uint8_t* comp, size_t n, uint8_t* dst, size_t cap) {
     void* dctx = Z.createDCtx();
-    int64_t r = decompress_one_frame(dctx, comp, n, dst, cap, Z.DStreamInSize(), Z.DStreamOutSize());
+    int64_t r = decompress_one_frame(dctx, comp, n, dst, cap, Z.DStreamInSize(), Z.DStreamOutSize(), NULL, 0);
     Z.freeDCtx(dctx);
     return r;
+}
+
+/* The two frame loops again, every frame with the same raw-content prefix (compress_with_prefix / decompress_with_prefix). */
+int64_t zkr_compress_frames_prefix(const uint8_t* src, size_t n, uint32_t frame_size, int level, int checksum,
+                                   uint8_t* dst, size_t slot, int64_t* sizes, uint32_t n_frames, int nthreads,
+                                   const uint8_t* prefix, size_t prefix_len) {
+    job j; memset(&j, 0, sizeof j);
+    j.src = src; j.n = n; j.frame_size = frame_size; j.level = level; j.checksum = checksum;
+    j.dst = dst; j.slot = slot; j.sizes = sizes; j.n_frames = n_frames; j.prefix = prefix; j.prefix_len = prefix_len;
+    run(compress_worker, &j, nthreads);
+    return j.err;
+}
+int64_t zkr_decompress_frames_prefix(const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off, uint32_t n_frames,
+                                     uint8_t* dst, int64_t* sizes, int nthreads, const uint8_t* prefix, size_t prefix_len) {
+    job j; memset(&j, 0, sizeof j);
+    j.src = comp; j.c_off = c_off; j.d_off = d_off; j.n_frames = n_frames; j.dst = dst; j.sizes = sizes;
+    j.prefix = prefix; j.prefix_len = prefix_len;
+    run(decompress_worker, &j, nthreads);
+    return j.err;
+}
+
+/* ZSTD_compress(): one-shot frame with a pledged size -> Frame_Content_Size (and Single_Segment when it fits the window). */
+int64_t zkr_compress_simple(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int level) {
+    size_t r = Z.compress(dst, cap, src, n, level);
+    if (Z.isError(r)) return -(int64_t)Z.getErrorCode(r);
+    return (int64_t)r;
 }

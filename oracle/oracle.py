@@ -65,6 +65,12 @@ def ref_lib():
                                               ctypes.c_uint32, _u8p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
         lib.zkr_decompress_any.restype = ctypes.c_int64
         lib.zkr_decompress_any.argtypes = [_u8p, ctypes.c_size_t, _u8p, ctypes.c_size_t]
+        lib.zkr_compress_frames_prefix.restype = ctypes.c_int64
+        lib.zkr_compress_frames_prefix.argtypes = lib.zkr_compress_frames.argtypes + [_u8p, ctypes.c_size_t]
+        lib.zkr_decompress_frames_prefix.restype = ctypes.c_int64
+        lib.zkr_decompress_frames_prefix.argtypes = lib.zkr_decompress_frames.argtypes + [_u8p, ctypes.c_size_t]
+        lib.zkr_compress_simple.restype = ctypes.c_int64
+        lib.zkr_compress_simple.argtypes = [_u8p, ctypes.c_size_t, _u8p, ctypes.c_size_t, ctypes.c_int]
         path = os.environ.get("ZK_LIBZSTD", SYSTEM_LIBZSTD)
         rc = lib.zkr_open(path.encode())
         if rc != 0:
@@ -84,6 +90,8 @@ def orc_lib():
         lib.zko_xxh64.argtypes = [_u8p, ctypes.c_size_t, ctypes.c_uint64]
         lib.zko_frame_stats.restype = ctypes.c_int64
         lib.zko_frame_stats.argtypes = [_u8p, ctypes.c_size_t, ctypes.c_void_p]
+        lib.zko_decompress_ex.restype = ctypes.c_int64
+        lib.zko_decompress_ex.argtypes = [_u8p, ctypes.c_size_t, _u8p, ctypes.c_size_t, ctypes.c_int, _u8p, ctypes.c_size_t, ctypes.c_void_p]
         _orc = lib
     return _orc
 
@@ -99,7 +107,7 @@ def _as_u8(buf) -> np.ndarray:
     return np.frombuffer(bytes(buf), dtype=np.uint8)
 
 
-def ref_compress_frames(data, frame_size: int = 0x200000, level: int = 0, checksum: bool = False, threads: int = 1):
+def ref_compress_frames(data, frame_size: int = 0x200000, level: int = 0, checksum: bool = False, threads: int = 1, prefix=None):
     """-> (list[bytes] frames, c_sizes, d_sizes) exactly as RawEncoder+FrameSizePolicy::Uncompressed would emit
     (encode.rs:311-354, 438-472, 528-544).  Empty input -> zero frames... except that the reference's
     finish() always ends one (possibly empty) frame (encode.rs:755-756); callers add that themselves."""
@@ -113,8 +121,13 @@ def ref_compress_frames(data, frame_size: int = 0x200000, level: int = 0, checks
     slot = lib.zkr_compress_bound(min(frame_size, n)) + 64
     dst = np.empty(n_frames * slot, dtype=np.uint8)
     sizes = (ctypes.c_int64 * n_frames)()
-    rc = lib.zkr_compress_frames(_ptr(src), n, frame_size, level, int(checksum), _ptr(dst), slot, sizes, n_frames,
-                                 threads)
+    if prefix is not None:                       # compress_with_prefix: the same prefix for every frame (encode.rs:332-338)
+        pf = _as_u8(prefix)
+        rc = lib.zkr_compress_frames_prefix(_ptr(src), n, frame_size, level, int(checksum), _ptr(dst), slot, sizes, n_frames,
+                                            threads, _ptr(pf), pf.size)
+    else:
+        rc = lib.zkr_compress_frames(_ptr(src), n, frame_size, level, int(checksum), _ptr(dst), slot, sizes, n_frames,
+                                     threads)
     if rc != 0:
         raise RuntimeError(f"libzstd compress error {rc}")
     frames = [dst[i * slot: i * slot + sizes[i]].tobytes() for i in range(n_frames)]
@@ -122,7 +135,7 @@ def ref_compress_frames(data, frame_size: int = 0x200000, level: int = 0, checks
     return frames, [int(s) for s in sizes], d_sizes
 
 
-def ref_decompress_frames(comp, c_off, d_off, threads: int = 1):
+def ref_decompress_frames(comp, c_off, d_off, threads: int = 1, prefix=None):
     """decompress frames given cumulative offsets -> (np.uint8 output, per-frame sizes or -code)"""
     lib = ref_lib()
     src = _as_u8(comp)
@@ -131,7 +144,11 @@ def ref_decompress_frames(comp, c_off, d_off, threads: int = 1):
     do = (ctypes.c_uint64 * (nf + 1))(*[int(x) for x in d_off])
     out = np.empty(max(1, int(d_off[-1])), dtype=np.uint8)
     sizes = (ctypes.c_int64 * max(nf, 1))()
-    lib.zkr_decompress_frames(_ptr(src), co, do, nf, _ptr(out), sizes, threads)
+    if prefix is not None:                       # decompress_with_prefix (decode.rs:211-214, 246-255)
+        pf = _as_u8(prefix)
+        lib.zkr_decompress_frames_prefix(_ptr(src), co, do, nf, _ptr(out), sizes, threads, _ptr(pf), pf.size)
+    else:
+        lib.zkr_decompress_frames(_ptr(src), co, do, nf, _ptr(out), sizes, threads)
     return out[: int(d_off[-1])], [int(sizes[i]) for i in range(nf)]
 
 
@@ -144,6 +161,22 @@ def ref_decompress_any(comp, cap: int):
     if r < 0:
         raise ZstdError(int(-r))
     return out[:r].tobytes()
+
+
+def ref_compress_simple(data, level: int = 3) -> bytes:
+    """ZSTD_compress(): a one-shot frame (Frame_Content_Size present; Single_Segment when the content fits the window)"""
+    lib = ref_lib()
+    src = _as_u8(data)
+    dst = np.empty(lib.zkr_compress_bound(src.size) + 64, dtype=np.uint8)
+    r = lib.zkr_compress_simple(_ptr(src), src.size, _ptr(dst), dst.size, level)
+    if r < 0:
+        raise ZstdError(int(-r))
+    return dst[:r].tobytes()
+
+
+def skippable_frame(payload: bytes, nibble: int = 0) -> bytes:
+    """a skippable frame (RFC 8878 3.1.2): magic 0x184D2A5? + size + payload"""
+    return struct.pack("<II", 0x184D2A50 | (nibble & 15), len(payload)) + payload
 
 
 class ZstdError(Exception):
@@ -161,6 +194,29 @@ def oracle_decompress(comp, cap: int, verify_checksum: bool = True) -> bytes:
     if r < 0:
         raise ZstdError(int(-r))
     return out[:r].tobytes()
+
+
+class SeqStats(ctypes.Structure):
+    _fields_ = [("rep_idx", ctypes.c_uint64 * 4)] + [(n, ctypes.c_uint64) for n in ("rep_ll0", "overlap", "explicit_offsets", "max_offset", "prefix_matches")]
+
+    def as_dict(self):
+        d = {n: int(getattr(self, n)) for n in ("rep_ll0", "overlap", "explicit_offsets", "max_offset", "prefix_matches")}
+        d.update({"rep1": int(self.rep_idx[0]), "rep2": int(self.rep_idx[1]), "rep3": int(self.rep_idx[2]), "rep1_minus_1": int(self.rep_idx[3])})
+        return d
+
+
+def oracle_decompress_ex(comp, cap: int, prefix=None, verify_checksum: bool = True):
+    """restated decoder with an optional raw-content prefix -> (bytes, sequence statistics dict)"""
+    lib = orc_lib()
+    src = _as_u8(comp)
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    ss = SeqStats()
+    pf = _as_u8(prefix) if prefix is not None else None
+    r = lib.zko_decompress_ex(_ptr(src), src.size, _ptr(out), cap, int(verify_checksum), _ptr(pf) if pf is not None else None,
+                              pf.size if pf is not None else 0, ctypes.byref(ss))
+    if r < 0:
+        raise ZstdError(int(-r))
+    return out[:r].tobytes(), ss.as_dict()
 
 
 def oracle_xxh64(data, seed: int = 0) -> int:

@@ -29,6 +29,7 @@
 #define ZE_WINDOW_TOO_LARGE 16
 #define ZE_CORRUPTION 20
 #define ZE_CHECKSUM_WRONG 22
+#define ZE_DICT_CORRUPTED 30   /* libzstd: Treeless literals with no Huffman table yet (ZSTD_decodeLiteralsBlock: litEntropy == 0) */
 #define ZE_DICT_WRONG 32
 #define ZE_DST_TOO_SMALL 70
 #define ZE_SRC_SIZE_WRONG 72
@@ -262,6 +263,18 @@ static const int16_t LL_DEFAULT[36] = {4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2
 static const int16_t ML_DEFAULT[53] = {1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1};
 static const int16_t OF_DEFAULT[29] = {1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1};
 
+/* Sequence-level statistics of a decode (tests: which repeat-offset cases / offset ranges an archive exercises). */
+typedef struct {
+    uint64_t rep_idx[4];        /* repeat-offset uses by resolved index: 0 rep1, 1 rep2, 2 rep3, 3 rep1-1 (code 3 with litLen == 0) */
+    uint64_t rep_ll0;           /* repeat codes met with litLen == 0 (index shifted by one) */
+    uint64_t overlap;           /* matches with offset < matchLength */
+    uint64_t explicit_offsets;
+    uint64_t max_offset;        /* largest match distance */
+    uint64_t prefix_matches;    /* matches reaching before the start of the frame (only legal with a prefix) */
+} zko_seq_stats;
+static __thread zko_seq_stats* g_ss = NULL;
+static __thread const uint8_t* g_prefix = NULL; static __thread size_t g_prefix_len = 0;
+
 /* per-frame decoding context (entropy tables persist across blocks of a frame) */
 typedef struct {
     huf_table huf;
@@ -269,6 +282,7 @@ typedef struct {
     int have_ll, have_of, have_ml;
     uint32_t rep[3];
     uint64_t window;
+    const uint8_t* prefix; size_t prefix_len;   /* raw-content prefix (ZSTD_DCtx_refPrefix; decode.rs:211-214): history before the frame */
 } frame_ctx;
 
 static int64_t read_seq_table(fse_table* t, int* have, int mode, const uint8_t* p, size_t n,
@@ -319,7 +333,7 @@ static int64_t decode_compressed_block(frame_ctx* fc, const uint8_t* p, size_t n
             int64_t r = huf_read_table(&fc->huf, q, qn);
             if (r < 0) return r;
             q += r; qn -= (size_t)r;
-        } else if (!fc->huf.valid) FAIL(ZE_CORRUPTION);
+        } else if (!fc->huf.valid) FAIL(ZE_DICT_CORRUPTED);
         if (streams == 1) {
             if (huf_decode_stream(&fc->huf, q, qn, litbuf, regen)) FAIL(ZE_CORRUPTION);
         } else {
@@ -376,9 +390,10 @@ static int64_t decode_compressed_block(frame_ctx* fc, const uint8_t* p, size_t n
         if (b.pos < 0) FAIL(ZE_CORRUPTION);
         /* repeat offsets */
         uint32_t off;
-        if (ov > 3) { off = ov - 3; fc->rep[2] = fc->rep[1]; fc->rep[1] = fc->rep[0]; fc->rep[0] = off; }
+        if (ov > 3) { off = ov - 3; fc->rep[2] = fc->rep[1]; fc->rep[1] = fc->rep[0]; fc->rep[0] = off; if (g_ss) g_ss->explicit_offsets++; }
         else {
             uint32_t idx = ov - 1 + (llen == 0);
+            if (g_ss) { g_ss->rep_idx[idx]++; g_ss->rep_ll0 += llen == 0; }
             if (idx == 0) off = fc->rep[0];
             else {
                 off = idx == 3 ? fc->rep[0] - 1 : fc->rep[idx];
@@ -391,8 +406,12 @@ static int64_t decode_compressed_block(frame_ctx* fc, const uint8_t* p, size_t n
         if (lpos + llen > regen) FAIL(ZE_CORRUPTION);
         if (out_pos + llen + mlen > out_cap) FAIL(ZE_DST_TOO_SMALL);
         memcpy(out_base + out_pos, lit + lpos, llen); lpos += llen; out_pos += llen;
-        if (off > out_pos) FAIL(ZE_CORRUPTION);
-        for (uint32_t k = 0; k < mlen; k++) out_base[out_pos + k] = out_base[out_pos + k - off];
+        if (off > out_pos + fc->prefix_len) FAIL(ZE_CORRUPTION);
+        if (g_ss) { g_ss->overlap += off < mlen; if (off > g_ss->max_offset) g_ss->max_offset = off; g_ss->prefix_matches += off > out_pos; }
+        for (uint32_t k = 0; k < mlen; k++) {
+            size_t at = out_pos + k;
+            out_base[at] = at >= off ? out_base[at - off] : fc->prefix[fc->prefix_len - (off - at)];
+        }
         out_pos += mlen;
     }
     if (b.pos != 0) FAIL(ZE_CORRUPTION);
@@ -414,6 +433,7 @@ static int64_t decode_one_frame(const uint8_t* src, size_t n, uint8_t* dst, size
     frame_ctx* fc = (frame_ctx*)calloc(1, sizeof(frame_ctx));
     if (!fc) FAIL(64);
     fc->rep[0] = 1; fc->rep[1] = 4; fc->rep[2] = 8;
+    fc->prefix = g_prefix; fc->prefix_len = g_prefix ? g_prefix_len : 0;   /* re-applied to every frame (decode.rs:246-255) */
     int64_t rc = 0;
 #define FFAIL(code) do { rc = -(int64_t)(code); goto done; } while (0)
     if (!single) {
@@ -501,6 +521,17 @@ int64_t zko_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, i
         pos += used; out += (size_t)r;
     }
     return (int64_t)out;
+}
+
+/* zko_decompress with a raw-content prefix for every frame (decompress_with_prefix, decode.rs:201-270) and/or
+ * sequence statistics.  prefix / ss may be NULL. */
+int64_t zko_decompress_ex(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int verify_checksum,
+                          const uint8_t* prefix, size_t prefix_len, zko_seq_stats* ss) {
+    if (ss) memset(ss, 0, sizeof *ss);
+    g_ss = ss; g_prefix = prefix; g_prefix_len = prefix_len;
+    int64_t r = zko_decompress(src, n, dst, cap, verify_checksum);
+    g_ss = NULL; g_prefix = NULL; g_prefix_len = 0;
+    return r;
 }
 
 /* Frame-structure statistics used by tests to confirm coverage of the format matrix. */

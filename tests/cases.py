@@ -73,6 +73,76 @@ def check_corruption_is_detected(ctx, trials: int = 24):
     for blob in (good[:-7], good[: len(good) // 2], b"\x00" * 64, good[:4]):
         out, st, rc = decode_frames(ctx, [blob], ds, verify=True)
         assert rc != 0
+    check_crafted_frames_rejected(ctx)
+
+
+class _BackBits:
+    """writer for zstd's backward bitstreams (RFC 8878 4.1): fields in the order they are WRITTEN, then the end mark"""
+
+    def __init__(self):
+        self.acc, self.n = 0, 0
+
+    def put(self, value: int, bits: int):
+        self.acc |= (value & ((1 << bits) - 1)) << self.n; self.n += bits
+
+    def finish(self) -> bytes:
+        self.put(1, 1)
+        return self.acc.to_bytes((self.n + 7) // 8, "little")
+
+
+def _frame(blocks) -> bytes:
+    """magic, FHD 0 (no FCS, no checksum), window descriptor 0x50 (1 MiB), then (type, content[, regen]) blocks"""
+    out = bytearray(b"\x28\xb5\x2f\xfd\x00\x50")
+    for i, blk in enumerate(blocks):
+        btype, content = blk[0], blk[1]
+        size = blk[2] if btype == 1 else len(content)
+        out += ((size << 3) | (btype << 1) | int(i == len(blocks) - 1)).to_bytes(3, "little") + content
+    return bytes(out)
+
+
+def crafted_overflow_frame() -> bytes:
+    """40 000 sequences whose literal lengths sum to exactly 2^32 -- the wrapped totals look valid, every
+    intermediate sum is far out of range.  Literals: Raw, 0 bytes; all three tables RLE (LL code 35 = 65536 + 16 bits,
+    OF code 1 = repeat offsets, ML code 0 = 3)."""
+    nseq = 40_000
+    lls = [107_374] * (nseq - 1)
+    lls.append((1 << 32) - sum(lls))
+    assert 65_536 <= lls[-1] <= 131_071
+    bw = _BackBits()
+    for ll in reversed(lls):                      # the decoder reads OF, ML, LL extra bits of the FIRST sequence first
+        bw.put(ll - 65_536, 16); bw.put(0, 1)
+    body = bytes([0x00]) + bytes([0xFF, (nseq - 0x7F00) & 0xFF, (nseq - 0x7F00) >> 8]) + bytes([0x54, 35, 1, 0]) + bw.finish()
+    assert len(body) <= 128 << 10
+    return _frame([(2, body)])
+
+
+def crafted_frames():
+    """-> list of (name, frame bytes, decompressed-size claim) that libzstd rejects as corrupted"""
+    treeless_first = _frame([(2, bytes([0x43, 0x40, 0x00, 0x01, 0x00]))])          # Treeless literals in the first block (ADVICE r1, high)
+    # Repeat_Mode sequence tables in the first block with sequences: raw literals (4 bytes), nseq 1, modes LL=repeat
+    repeat_first = _frame([(2, bytes([0x20]) + b"abcd" + bytes([0x01, 0xC0]) + bytes([0x01, 0x01]))])
+    # a valid raw block, THEN a treeless block: the count pass must also see the missing tree in later blocks
+    treeless_later = _frame([(0, b"hello world"), (2, bytes([0x43, 0x40, 0x00, 0x01, 0x00]))])
+    return [("overflow", crafted_overflow_frame(), 120_000), ("treeless_first", treeless_first, 4), ("repeat_first", repeat_first, 8),
+            ("treeless_later", treeless_later, 15)]
+
+
+def check_crafted_frames_rejected(ctx):
+    """hand-built invalid frames: libzstd and the restatement say corruption; the codec must say so too, must not touch memory
+    outside its buffers (tests/emul/asan_check.py runs this under ASan), and must still decode a good frame in the SAME batch"""
+    x = np.frombuffer(golden_bytes("dickens_96k.txt")[:20_000], dtype=np.uint8)
+    good, gcs, gds = O.ref_compress_frames(x, 20_000, 3, True)
+    for name, fr, claim in crafted_frames():
+        for fn in (O.ref_decompress_any, O.oracle_decompress):
+            try:
+                fn(fr, 1 << 20)
+                raise AssertionError(f"{name}: the oracle accepted a crafted frame")
+            except O.ZstdError as e:
+                code = e.code
+                assert code == (30 if name.startswith("treeless") else 20), (name, code)     # libzstd: dictionary_corrupted for a missing tree
+        out, st, rc = decode_frames(ctx, [good[0], fr, good[0]], [gds[0], claim, gds[0]], verify=True)
+        assert rc == -code and list(st) == [0, -code, 0], (name, rc, list(st))
+        assert out[:20_000] == x.tobytes() and out[20_000 + claim:] == x.tobytes()
 
 
 # ------------------------------------------------------------------------------------------------ API: encode side

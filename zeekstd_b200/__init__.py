@@ -140,6 +140,8 @@ class Context:
         total = int(do[-1])
         if out is None:
             out = np.empty(total + 64, dtype=np.uint8)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= total):
+            raise ValueError(f"out: need a C-contiguous np.uint8 array of at least {total} bytes")
         st = np.zeros(max(nf, 1), dtype=np.int32)
         nd = None if need is None else np.ascontiguousarray(need, dtype=np.uint32)
         if nd is not None and len(nd) != nf:

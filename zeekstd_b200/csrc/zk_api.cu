@@ -53,6 +53,7 @@ extern "C" const char* zk_error_name(int32_t rc) {
     case -16: return "Frame requires too much memory for decoding";
     case -20: return "Data corruption detected";
     case -22: return "Restored data doesn't match checksum";
+    case -30: return "Dictionary is corrupted";
     case -32: return "Dictionary mismatch";
     case -42: return "Parameter is out of bound";
     case -64: return "Allocation error : not enough memory";

@@ -57,6 +57,7 @@ enum ZkZstdCode : int {
     ZKZ_WINDOW_TOO_LARGE = 16,
     ZKZ_CORRUPTION = 20,
     ZKZ_CHECKSUM_WRONG = 22,
+    ZKZ_DICT_CORRUPTED = 30,         // what libzstd reports for Treeless literals before any Huffman table (litEntropy == 0)
     ZKZ_DICT_WRONG = 32,
     ZKZ_PARAM_OUT_OF_BOUND = 42,
     ZKZ_MEMORY_ALLOCATION = 64,

@@ -141,10 +141,23 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
 
 struct ZkCountEmit {
     uint32_t nb = 0, nlit = 0, nseq = 0, nhuf = 0, nsqb = 0;
+    // Treeless literals / Repeat_Mode tables must refer to something defined earlier in the same zstd frame.  This is
+    // checked HERE so that the fill pass (which reserves slots of huf_list / seq_list from these counts) cannot fail
+    // after the count pass succeeded: every reserved work-list slot is always written.
+    uint32_t have = 0;            // bit 0 Huffman tree, bits 1..3 LL / OF / ML table
     __device__ int operator()(const ZkBlkInfo& bi) {
         nb++;
+        if (bi.flags & ZKB_FIRST) have = 0;
         if (bi.type == 2) {
+            if (bi.lit_type == 3 && !(have & 1u)) return ZKZ_DICT_CORRUPTED;
+            if (bi.lit_type == 2) have |= 1u;
             if (bi.lit_type >= 2) { nlit += (bi.lit_size + 15u) & ~15u; nhuf++; }
+            if (bi.nseq) {
+                const uint32_t ml_m = (bi.modes >> 2) & 3, of_m = (bi.modes >> 4) & 3, ll_m = (bi.modes >> 6) & 3;
+                if (ll_m == 3) { if (!(have & 2u)) return ZKZ_CORRUPTION; } else have |= 2u;
+                if (of_m == 3) { if (!(have & 4u)) return ZKZ_CORRUPTION; } else have |= 4u;
+                if (ml_m == 3) { if (!(have & 8u)) return ZKZ_CORRUPTION; } else have |= 8u;
+            }
             nseq += bi.nseq; nsqb += bi.nseq != 0;
         }
         return 0;
@@ -164,7 +177,7 @@ struct ZkFillEmit {
         if (bi.flags & ZKB_FIRST) { huf_ref = ll_ref = of_ref = ml_ref = -1; }
         b.huf_ref = -1; b.ll_ref = -1; b.of_ref = -1; b.ml_ref = -1;
         if (bi.type == 2) {
-            if (bi.lit_type == 3) { if (huf_ref < 0) return ZKZ_CORRUPTION; b.huf_ref = huf_ref; }
+            if (bi.lit_type == 3) { if (huf_ref < 0) return ZKZ_DICT_CORRUPTED; b.huf_ref = huf_ref; }
             if (bi.lit_type == 2) huf_ref = (int32_t)bidx;
             if (bi.lit_type >= 2) { lit += (bi.lit_size + 15u) & ~15u; b.lit_kind = 2; huf_list[hufi++] = bidx; }
             else if (bi.lit_type == 0) { b.lit_kind = 0; b.lit_src = bi.src + bi.lit_hdr; }
@@ -370,11 +383,13 @@ __device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkSeqTabs& tb, con
             }
         }
         lit_end += llv; out_end += llv + mlv;
+        // bounded after EVERY sequence (one step adds < 2^18, so neither sum can wrap past 2^32 unnoticed): the exec
+        // kernel uses the intermediate sums as literal-source and output positions
+        if (lit_end > blk.lit_size || out_end > ZK_BLOCK_MAX) { st = ZKZ_CORRUPTION; break; }
         o_lit[i] = lit_end; o_out[i] = out_end; o_off[i] = off;
     }
-    if (br.bp != 0) st = ZKZ_CORRUPTION;
-    if (lit_end > blk.lit_size) st = ZKZ_CORRUPTION;
-    else if (out_end + (blk.lit_size - lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
+    if (!st && br.bp != 0) st = ZKZ_CORRUPTION;
+    if (!st && out_end + (blk.lit_size - lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
     a.blocks[bidx].rep_out[0] = r0; a.blocks[bidx].rep_out[1] = r1; a.blocks[bidx].rep_out[2] = r2;
     a.blocks[bidx].regen = out_end + (blk.lit_size - lit_end);
     return st;
@@ -399,8 +414,9 @@ __global__ void __launch_bounds__(32 * ZK_SEQ_WARPS) zk_seq_kernel(ZkDecodeArgs 
         uint32_t my = first + lane;
         if (lane < ZK_SEQ_LPW && my < n) {
             uint32_t bidx = a.seq_list[my];
-            ZkBlock blk = a.blocks[bidx];
-            if (a.entries[blk.entry].status == 0) {
+            ZkBlock blk; blk.entry = 0xFFFFFFFFu;
+            if (bidx < a.cap_blocks) blk = a.blocks[bidx];          // always: every reserved slot is written by the scan kernel
+            if (blk.entry < a.n_entries && a.entries[blk.entry].status == 0) {
                 int st = zk_decode_block_sequences(slots[warp * ZK_SEQ_LPW + lane], *tb, a, blk, bidx, a.comp + a.c_off[blk.entry]);
                 a.blocks[bidx].status = st ? -st : 0;
             }
@@ -469,6 +485,7 @@ __device__ uint32_t zk_read_huf_weights(ZkHufSlot& sl, const uint8_t* p, uint32_
             s2 = sl.wbase[s2] + br.read(sl.wnb[s2]);
             if (br.bp < 0) { sl.weights[nw++] = sl.wsym[s1]; break; }
         }
+        if (nw > 255) return 0;                    // at most 255 explicit weights (+ the implied one = 256 symbols)
     }
     uint32_t total = 0, n_w1 = 0;
     for (int i = 0; i < nw; i++) {
@@ -537,10 +554,14 @@ __global__ void __launch_bounds__(32) zk_huf_kernel(ZkDecodeArgs a) {
         bool live = false;
         if (active) {
             bidx = a.huf_list[my];
-            blk = a.blocks[bidx];
-            live = a.entries[blk.entry].status == 0;
-            ebase = a.comp + a.c_off[blk.entry];
-            zk_parse_lit_hdr(ebase + blk.src, blk.size, lh);      // validated by the scan kernel
+            if (bidx < a.cap_blocks) {                              // always: every reserved slot is written by the scan kernel
+                blk = a.blocks[bidx];
+                live = blk.entry < a.n_entries && a.entries[blk.entry].status == 0;
+            }
+            if (live) {
+                ebase = a.comp + a.c_off[blk.entry];
+                zk_parse_lit_hdr(ebase + blk.src, blk.size, lh);  // validated by the scan kernel
+            }
         }
         // 1. tree description (own block, or the block a Treeless block refers to) -- one lane per block
         if (live && stream == 0) {
