@@ -16,6 +16,40 @@ from util import decode_frames, golden_bytes, golden_meta, offsets, split_frames
 INPUT = golden_bytes("dickens_96k.txt")[:12_345]       # plays the role of lib.rs's INPUT (the reference uses its own source text)
 
 
+# ------------------------------------------------------------------------------------------------ coverage bookkeeping
+# Every archive a test feeds to the codec's DECODER is also walked by the restatement (oracle.frame_stats, and -- below
+# COVER_SEQ_BYTES -- decoded by it for the sequence-level statistics); the totals are asserted cell by cell at the end of
+# each suite (check_coverage_matrix): the decoder coverage matrix of SURVEY.md 8a is then proven to have been exercised
+# on the build under test, not assumed.
+COVERAGE: dict = {}
+COVER_SEQ_BYTES = 48 << 20
+MATRIX_CELLS = ("n_raw", "n_rle", "n_comp", "lit_raw", "lit_rle", "lit_huf", "lit_treeless", "lit_1stream", "lit_4stream", "huf_direct", "huf_fse",
+                "mode_predef", "mode_rle", "mode_fse", "mode_repeat", "nseq0_blocks", "checksum_frames", "single_segment_frames",
+                "skippable_frames", "multi_frame_entries", "rep1", "rep2", "rep3", "rep1_minus_1", "rep_ll0", "overlap", "dict_id_rejected",
+                "frames_over_2MiB", "offsets_over_1MiB")
+
+
+def cover(entries, d_total: int | None = None, prefix=None):
+    """entries: list of the compressed bytes of seek-table entries that were decoded by the codec under test"""
+    blob = b"".join(entries)
+    for k, v in O.frame_stats(blob).items():
+        COVERAGE[k] = COVERAGE.get(k, 0) + v
+    for e in entries:
+        fs = O.frame_stats(e)
+        COVERAGE["multi_frame_entries"] = COVERAGE.get("multi_frame_entries", 0) + int(fs["zstd_frames"] > 1)
+    if d_total is not None and d_total <= COVER_SEQ_BYTES:
+        _, ss = O.oracle_decompress_ex(blob, d_total + 1, prefix=prefix)
+        for k, v in ss.items():
+            COVERAGE[k] = max(COVERAGE.get(k, 0), v) if k == "max_offset" else COVERAGE.get(k, 0) + v
+        COVERAGE["offsets_over_1MiB"] = COVERAGE.get("offsets_over_1MiB", 0) + int(ss["max_offset"] > (1 << 20))
+
+
+def check_coverage_matrix(cells=MATRIX_CELLS):
+    missing = [c for c in cells if COVERAGE.get(c, 0) <= 0]
+    assert not missing, f"decoder coverage matrix: cells never exercised in this run: {missing}; totals {COVERAGE}"
+    return {c: COVERAGE[c] for c in cells}
+
+
 # ------------------------------------------------------------------------------------------------ raw codec parity
 def check_decode_matches_libzstd(ctx, data: np.ndarray, frame_size: int, level: int, checksum: bool):
     """libzstd-compressed frames must decode bit-exactly (== ZSTD_decompressStream output == the input)"""
@@ -23,6 +57,9 @@ def check_decode_matches_libzstd(ctx, data: np.ndarray, frame_size: int, level: 
     out, st, rc = decode_frames(ctx, frames, ds, verify=True)
     assert rc == 0 and not st.any(), (rc, st[st != 0][:5])
     assert out == data.tobytes()
+    cover(frames, data.size)
+    if frame_size > (2 << 20) and data.size > (2 << 20):
+        COVERAGE["frames_over_2MiB"] = COVERAGE.get("frames_over_2MiB", 0) + 1
 
 
 def check_compress_roundtrip(ctx, data: np.ndarray, frame_size: int, level: int, checksum: bool):
@@ -46,9 +83,11 @@ def check_golden_archives(ctx):
     src = golden_bytes("dickens_96k.txt")
     for name, info in meta["archives"].items():
         a = golden_bytes(name + ".zst")
-        dec = zk.Decoder(zk.BytesWrapper(a) if False else zk.DecodeOptions(a, ctx))
+        dec = zk.Decoder(zk.DecodeOptions(a, ctx))
         assert dec.seek_table().num_frames() == info["num_frames"]
         assert dec.read_all() == src[: info["src_bytes"]], name
+        st = O.OracleSeekTable.parse(a, "foot")
+        cover([a[st.c[i]: st.c[i + 1]] for i in range(st.num_frames())], info["src_bytes"])
 
 
 def check_corruption_is_detected(ctx, trials: int = 24):
@@ -125,6 +164,104 @@ def crafted_frames():
     treeless_later = _frame([(0, b"hello world"), (2, bytes([0x43, 0x40, 0x00, 0x01, 0x00]))])
     return [("overflow", crafted_overflow_frame(), 120_000), ("treeless_first", treeless_first, 4), ("repeat_first", repeat_first, 8),
             ("treeless_later", treeless_later, 15)]
+
+
+# --- hand-built VALID frames for the cells of the matrix libzstd's encoder does not reach on demand ------------------
+_LL_BITS = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+_ML_BITS = [0] * 32 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+
+
+def _lit_header(kind: int, regen: int) -> bytes:
+    """Literals_Section_Header for Raw (0) / RLE (1) literals"""
+    if regen < 32:
+        return bytes([(regen << 3) | kind])
+    if regen < 4096:
+        return ((regen << 4) | (1 << 2) | kind).to_bytes(2, "little")
+    return ((regen << 4) | (3 << 2) | kind).to_bytes(3, "little")
+
+
+def _nseq_bytes(n: int) -> bytes:
+    if n < 128:
+        return bytes([n])
+    if n < 0x7F00:
+        return bytes([128 + (n >> 8), n & 0xFF])
+    return bytes([0xFF, (n - 0x7F00) & 0xFF, (n - 0x7F00) >> 8])
+
+
+def _rle_seq_block(lit_section: bytes, codes, seqs, repeat_tables: bool = False) -> bytes:
+    """a Compressed block whose three sequence tables are RLE (one code each; the values vary through the extra bits only),
+    or Repeat_Mode of the previous block's tables.  codes = (ll_code, of_code, ml_code); seqs = [(ll_x, of_x, ml_x)] extra bits"""
+    llc, ofc, mlc = codes
+    bw = _BackBits()
+    for llx, ofx, mlx in reversed(seqs):          # the decoder reads OF, ML, LL of the first sequence first
+        bw.put(llx, _LL_BITS[llc]); bw.put(mlx, _ML_BITS[mlc]); bw.put(ofx, ofc)
+    tables = bytes([0xFC]) if repeat_tables else bytes([0x54, llc, ofc, mlc])
+    return lit_section + _nseq_bytes(len(seqs)) + tables + bw.finish()
+
+
+def crafted_valid_frame(seed: int = 1):
+    """One zstd frame, five blocks: Raw history; RLE literals + RLE-mode tables (explicit offsets); Raw literals with
+    litLen == 0 repeat codes (rep2/rep3 shifted and the rep1-1 case); the same tables again through Repeat_Mode; an RLE block.
+    -> frame bytes (libzstd is the judge of what it decodes to)"""
+    rng = np.random.default_rng(seed)
+    hist = rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    # B: 40 sequences, litLen 16/17 of 'Q' (RLE literals), offset code 9 (509..1020), matchLen 35/36
+    seqs_b = [(int(rng.integers(2)), int(rng.integers(512)), int(rng.integers(2))) for _ in range(40)]
+    n_lit_b = sum(16 + s[0] for s in seqs_b) + 5                      # five trailing literals
+    blk_b = _rle_seq_block(_lit_header(1, n_lit_b) + b"Q", (16, 9, 32), seqs_b)
+    # C: litLen 0 (code 0), offset code 1 -> Offset_Value 2/3 -> with litLen == 0: rep3 / rep1-1; matchLen 8 (code 5)
+    seqs_c = [(0, int(rng.integers(2)), 0) for _ in range(30)]
+    blk_c = _rle_seq_block(_lit_header(0, 3) + b"xyz", (0, 1, 5), seqs_c)
+    # D: Repeat_Mode for all three tables (the RLE tables of C), offset values 2/3 again, raw literals
+    seqs_d = [(0, int(rng.integers(2)), 0) for _ in range(20)]
+    blk_d = _rle_seq_block(_lit_header(0, 0), (0, 1, 5), seqs_d, repeat_tables=True)
+    return _frame([(0, hist), (2, blk_b), (2, blk_c), (2, blk_d), (1, b"\x7f", 777)])
+
+
+def check_special_entries(ctx):
+    """cells of SURVEY.md 8a's matrix that need particular producers: hand-built RLE literals / RLE + Repeat tables /
+    rep1-1; ZSTD_compress() one-shot frames (Single_Segment, every Frame_Content_Size width); skippable frames before,
+    between and after zstd frames of one seek-table entry; several zstd frames per entry; RLE blocks; direct Huffman
+    weights; a non-zero Dictionary_ID (rejected with dictionary_wrong, like libzstd without a dictionary)"""
+    rng = np.random.default_rng(5)
+    text = np.frombuffer(golden_bytes("dickens_96k.txt"), dtype=np.uint8)
+    entries, wants = [], []
+
+    def add(entry: bytes):
+        want = O.ref_decompress_any(entry, 4 << 20)                    # libzstd is the reference for what an entry decodes to
+        assert O.oracle_decompress(entry, 4 << 20) == want
+        entries.append(entry); wants.append(want)
+
+    add(crafted_valid_frame(1)); add(crafted_valid_frame(2))
+    for n in (0, 1, 255, 256, 300, 65_791, 65_792, 90_000):            # FCS field widths 1 / 2 (+256) / 4 bytes
+        add(O.ref_compress_simple(text[:n], 3))
+    one = O.ref_compress_simple(text[:5000], 1); two = O.ref_compress_frames(text[5000:40_000], 20_000, 3, True)[0]
+    add(O.skippable_frame(b"meta", 3) + one + O.skippable_frame(b"") + two[0] + two[1] + O.skippable_frame(b"x" * 100, 15))
+    add(O.skippable_frame(b"only skippable"))                          # an entry that decodes to nothing
+    add(O.ref_compress_frames(np.zeros(400_000, dtype=np.uint8), 400_000, 3, True)[0][0])            # RLE blocks
+    p = np.array([.4, .25, .15, .08, .05, .04, .02, .01])
+    add(O.ref_compress_frames(rng.choice(8, size=150_000, p=p).astype(np.uint8), 150_000, 1, False)[0][0])   # direct weights + treeless
+    ds = [len(w) for w in wants]
+    out, st, rc = decode_frames(ctx, entries, ds, verify=True)
+    assert rc == 0 and not st.any(), (rc, list(st))
+    assert out == b"".join(wants)
+    cover(entries, sum(ds))
+    # Dictionary_ID: flag 1 (one byte), ID 7, spliced into a valid frame header -> dictionary_wrong (32) in both decoders
+    good = O.ref_compress_frames(text[:3000], 3000, 3, False)[0][0]
+    assert good[4] & 3 == 0
+    bad = good[:4] + bytes([good[4] | 1, good[5], 7]) + good[6:]
+    for fn in (O.ref_decompress_any, O.oracle_decompress):
+        try:
+            fn(bad, 1 << 20); raise AssertionError("a frame with a Dictionary_ID was accepted")
+        except O.ZstdError as e:
+            assert e.code == 32
+    out, st, rc = decode_frames(ctx, [good, bad], [3000, 3000], verify=True)
+    assert rc == -32 and list(st) == [0, -32] and out[:3000] == text[:3000].tobytes()
+    bad0 = good[:4] + bytes([good[4] | 1, good[5], 0]) + good[6:]     # Dictionary_ID field present but zero: no dictionary needed
+    assert O.ref_decompress_any(bad0, 1 << 20) == text[:3000].tobytes()
+    out, st, rc = decode_frames(ctx, [bad0], [3000], verify=True)
+    assert rc == 0 and out == text[:3000].tobytes()
+    COVERAGE["dict_id_rejected"] = COVERAGE.get("dict_id_rejected", 0) + 1
 
 
 def check_crafted_frames_rejected(ctx):

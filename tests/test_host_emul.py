@@ -65,6 +65,10 @@ def test_corruption_detected(ctx):
     cases.check_corruption_is_detected(ctx, trials=12)
 
 
+def test_special_entries(ctx):
+    cases.check_special_entries(ctx)
+
+
 def test_cycle_tiny_buffers(ctx):
     cases.check_cycle_tiny_buffers(ctx)
     cases.check_cycle_tiny_buffers(ctx, zk.FrameSizePolicy.Uncompressed(777))
@@ -120,3 +124,8 @@ def test_libzstd_archive_through_decoder(ctx):
 
 def test_range_reads_stop_early(ctx):
     cases.check_range_reads_stop_early(ctx)
+
+
+def test_zz_decoder_coverage_matrix(ctx):
+    """runs last in this file: every cell of SURVEY.md 8a's matrix that fits emulator-sized inputs was decoded above"""
+    cases.check_coverage_matrix([c for c in cases.MATRIX_CELLS if c not in ("frames_over_2MiB", "offsets_over_1MiB")])
