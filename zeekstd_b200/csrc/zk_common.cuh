@@ -258,3 +258,110 @@ __device__ inline uint32_t zk_fse_read_ncount(const uint8_t* p, uint32_t n, int 
     *nsym_out = s; *log_out = al;
     return used;
 }
+
+// -------------------------------------------------------------------------------------------
+// Event = an mbarrier with an arrival count of one: every arrive completes a phase, so "something changed" wakes
+// whoever sleeps in try_wait on it (hardware sleep: a waiting warp issues nothing, and wakes ~60 cycles after the
+// arrive -- B300_MICROARCH.md, mbarrier).  A waiter re-checks its own condition after every wake-up; it first learns the
+// parity of the running phase (test_wait), THEN checks the condition, then sleeps on that parity, so a change between the
+// check and the sleep ends the sleep at once.  Two changes in that window would be missed; the time hint bounds that.
+// -------------------------------------------------------------------------------------------
+#ifndef ZK_EMUL
+__device__ __forceinline__ uint32_t zk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zk_event_init(unsigned long long* bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(zk_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void zk_event_signal(unsigned long long* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(zk_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ uint32_t zk_event_parity(unsigned long long* bar) {      // parity of the phase that is running now
+    uint32_t done0;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done0) : "r"(zk_smem_u32(bar)) : "memory");
+    return done0;                                                                     // phase of parity 0 complete <=> parity 1 is running
+}
+__device__ __forceinline__ bool zk_event_sleep(unsigned long long* bar, uint32_t parity, uint32_t hint_ns) {   // true: that phase has completed
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(zk_smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
+#else
+__device__ __forceinline__ void zk_event_init(unsigned long long* bar) { *bar = 0; }
+__device__ __forceinline__ void zk_event_signal(unsigned long long* bar) { *(volatile unsigned long long*)bar = *bar + 1; }
+__device__ __forceinline__ uint32_t zk_event_parity(unsigned long long* bar) { return (uint32_t)(*(volatile unsigned long long*)bar & 1); }
+__device__ __forceinline__ bool zk_event_sleep(unsigned long long* bar, uint32_t parity, uint32_t) { emu::yield(); return (uint32_t)(*(volatile unsigned long long*)bar & 1) != parity; }
+#endif
+
+// -------------------------------------------------------------------------------------------
+// XXH64 (A.8), seed 0, of p[0..len) by one warp; the result is valid in every lane.
+//
+// The four accumulators are four serial chains (acc = rotl(acc + in * P2, 31) * P1 per 32-byte stripe), so one frame
+// cannot go faster than about 40 cycles per stripe whatever the width of the machine.  What CAN be taken off that chain
+// is everything else: the warp loads 256 bytes (8 stripes) with one coalesced 8-byte load per lane, four iterations
+// ahead, every lane multiplies its own word by P2, and the chain (replicated in all lanes: lane L carries accumulator
+// L & 3) picks the products up by shuffle.  The first version (lanes 0..3 each loading their own words, unaligned, one
+// stripe at a time) ran at 330 cycles per stripe: 21.7 ms per GiB of 2 MiB frames against 28 ms for the whole LZ77
+// execution -- it was the most expensive kernel of a checksummed decode.
+// -------------------------------------------------------------------------------------------
+#define ZK_P1 0x9E3779B185EBCA87ull
+#define ZK_P2 0xC2B2AE3D27D4EB4Full
+#define ZK_P3 0x165667B19E3779F9ull
+#define ZK_P4 0x85EBCA77C2B2AE63ull
+#define ZK_P5 0x27D4EB2F165667C5ull
+__device__ __forceinline__ unsigned long long zk_rotl64(unsigned long long x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ unsigned long long zk_xx_round(unsigned long long acc, unsigned long long in) { return zk_rotl64(acc + in * ZK_P2, 31) * ZK_P1; }
+__device__ __forceinline__ unsigned long long zk_xx_merge(unsigned long long h, unsigned long long v) { return (h ^ zk_xx_round(0, v)) * ZK_P1 + ZK_P4; }
+__device__ __forceinline__ unsigned long long zk_ld_u64_unaligned(const uint8_t* p) {
+    uintptr_t a = (uintptr_t)p; uint32_t mis = (uint32_t)(a & 7);
+    const unsigned long long* q = (const unsigned long long*)(a - mis);
+    if (mis == 0) return q[0];
+    return (q[0] >> (mis * 8)) | (q[1] << (64 - mis * 8));
+}
+
+static __device__ __noinline__ unsigned long long zk_warp_xxh64(const uint8_t* p, uint32_t len, int lane) {
+    unsigned long long h;
+    uint32_t done = 0;
+    if (len >= 32) {
+        const int al = lane & 3;
+        unsigned long long acc = al == 0 ? ZK_P1 + ZK_P2 : (al == 1 ? ZK_P2 : (al == 2 ? 0ull : 0ull - ZK_P1));
+        const uint32_t iters = len >> 8;                                 // 256 bytes = 8 stripes per iteration
+        if (iters) {
+            const uint32_t mis = (uint32_t)((uintptr_t)p & 7), sh = mis * 8;
+            const unsigned long long* qa = (const unsigned long long*)(p - mis);       // aligned view; word i covers bytes [8i - mis, 8i + 8 - mis)
+            // with mis != 0 the last word read lies up to 7 bytes past p + 256 * iters: inside the buffer whenever len has a tail,
+            // inside the 16 bytes of padding every codec buffer carries otherwise
+            unsigned long long w0 = qa[lane], w1 = 0, w2 = 0, w3 = 0;
+            if (iters > 1) w1 = qa[32 + lane];
+            if (iters > 2) w2 = qa[64 + lane];
+            if (iters > 3) w3 = qa[96 + lane];
+            for (uint32_t it = 0; it < iters; it++) {
+                unsigned long long wn = 0;                                // four iterations ahead
+                if (it + 4 < iters) wn = qa[(size_t)(it + 4) * 32 + lane];
+                unsigned long long v = w0;
+                if (mis) {
+                    unsigned long long up = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+                    unsigned long long nx = it + 1 < iters ? __shfl_sync(0xFFFFFFFFu, w1, 0) : qa[(size_t)(it + 1) * 32];
+                    if (lane == 31) up = nx;
+                    v = (w0 >> sh) | (up << (64 - sh));
+                }
+                const unsigned long long prod = v * ZK_P2;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const unsigned long long x = __shfl_sync(0xFFFFFFFFu, prod, k * 4 + al);
+                    acc = zk_rotl64(acc + x, 31) * ZK_P1;
+                }
+                w0 = w1; w1 = w2; w2 = w3; w3 = wn;
+            }
+            done = iters << 8;
+        }
+        for (uint32_t i = done; i + 32 <= len; i += 32) acc = zk_xx_round(acc, zk_ld_u64_unaligned(p + i + al * 8));   // < 8 stripes
+        done += ((len - done) >> 5) << 5;
+        const unsigned long long v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1),
+                                 v3 = __shfl_sync(0xFFFFFFFFu, acc, 2), v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+        h = zk_rotl64(v1, 1) + zk_rotl64(v2, 7) + zk_rotl64(v3, 12) + zk_rotl64(v4, 18);
+        h = zk_xx_merge(h, v1); h = zk_xx_merge(h, v2); h = zk_xx_merge(h, v3); h = zk_xx_merge(h, v4);
+    } else h = ZK_P5;
+    h += (unsigned long long)len;
+    const uint8_t* q = p + done; uint32_t rem = len - done;
+    while (rem >= 8) { h ^= zk_xx_round(0, zk_ld_u64_unaligned(q)); h = zk_rotl64(h, 27) * ZK_P1 + ZK_P4; q += 8; rem -= 8; }
+    if (rem >= 4) { h ^= (unsigned long long)zk_ld_le32(q) * ZK_P1; h = zk_rotl64(h, 23) * ZK_P2 + ZK_P3; q += 4; rem -= 4; }
+    while (rem) { h ^= (unsigned long long)(*q) * ZK_P5; h = zk_rotl64(h, 11) * ZK_P1; q++; rem--; }
+    h ^= h >> 33; h *= ZK_P2; h ^= h >> 29; h *= ZK_P3; h ^= h >> 32;
+    return h;
+}

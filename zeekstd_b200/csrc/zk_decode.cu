@@ -751,6 +751,18 @@ __device__ __noinline__ void zk_warp_match(uint8_t* dst, uint32_t off, uint32_t 
     }
 }
 
+// the low min(k, 8) bytes of (lo, hi) -> p[0..): predicated byte stores at immediate offsets (k >= 1)
+__device__ __forceinline__ void zk_st_bytes8(uint8_t* p, uint32_t lo, uint32_t hi, uint32_t k) {
+    p[0] = (uint8_t)lo;
+    if (k > 1) p[1] = (uint8_t)(lo >> 8);
+    if (k > 2) p[2] = (uint8_t)(lo >> 16);
+    if (k > 3) p[3] = (uint8_t)(lo >> 24);
+    if (k > 4) p[4] = (uint8_t)hi;
+    if (k > 5) p[5] = (uint8_t)(hi >> 8);
+    if (k > 6) p[6] = (uint8_t)(hi >> 16);
+    if (k > 7) p[7] = (uint8_t)(hi >> 24);
+}
+
 // per-CTA view of the ring: position p (entry-relative) lives at ring[(p + mis) & mask], mis = (out address & 15)
 // so that 16-byte groups of the ring line up with 16-byte groups of HBM.
 struct ZkRing {
@@ -762,32 +774,47 @@ struct ZkRing {
         const uint32_t w0 = *(const uint32_t*)(ring + wi), w1 = *(const uint32_t*)(ring + ((wi + 4) & mask)), w2 = *(const uint32_t*)(ring + ((wi + 8) & mask));
         return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
     }
-    // lane-local match copy inside the ring: 16 bytes per step when the period allows it (a byte loop costs one dependent
-    // shared-memory round trip per byte, and this copy sits on the critical dependency chain of the frame)
+    // lane-local match copy inside the ring, 8 bytes per step when the period allows it.  This copy sits on the dependency
+    // chain of the frame AND was 40 % of all instructions of the kernel when it stored byte by byte through at() (address
+    // arithmetic, 64-bit shifts and loop control per byte: ~12 instructions a byte); without a wrap on either side it is three
+    // word loads, two funnel shifts and predicated byte stores at immediate offsets.
     __device__ __forceinline__ void copy_near(uint32_t dst, uint32_t src, uint32_t n) const {
-        if (dst - src >= 16) {
-            for (uint32_t i = 0; i < n; i += 16) {
-                unsigned long long v0 = ld8(src + i), v1 = ld8(src + i + 8);
-                const uint32_t k = n - i < 16 ? n - i : 16;
-                for (uint32_t q = 0; q < k; q++) {
-                    at(dst + i + q) = (uint8_t)(q < 8 ? v0 : v1);
-                    if (q < 8) v0 >>= 8; else v1 >>= 8;
+        const uint32_t size = mask + 1, di = (dst + mis) & mask, si = (src + mis) & mask;
+        if (dst - src >= 8) {
+            if (di + n <= size && si + n + 12 <= size) {
+                uint8_t* dp = ring + di; const uint32_t* sp = (const uint32_t*)(ring + (si & ~3u)); const uint32_t sh = (si & 3u) * 8u;
+                for (uint32_t i = 0; i < n; i += 8) {
+                    const uint32_t w0 = sp[0], w1 = sp[1], w2 = sp[2];
+                    zk_st_bytes8(dp, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), n - i);
+                    dp += 8; sp += 2;
+                }
+            } else {
+                for (uint32_t i = 0; i < n; i += 8) {
+                    unsigned long long v = ld8(src + i);
+                    const uint32_t k = n - i < 8 ? n - i : 8;
+                    for (uint32_t q = 0; q < k; q++) { at(dst + i + q) = (uint8_t)v; v >>= 8; }
                 }
             }
         } else for (uint32_t i = 0; i < n; i++) at(dst + i) = at(src + i);
     }
+    // store the low min(k, 8) bytes of (lo, hi) at positions [p, p + k) of the entry
+    __device__ __forceinline__ void st8(uint32_t p, uint32_t lo, uint32_t hi, uint32_t k) const {
+        const uint32_t di = (p + mis) & mask;
+        if (di + 8 <= mask + 1) zk_st_bytes8(ring + di, lo, hi, k);
+        else { unsigned long long v = (unsigned long long)lo | ((unsigned long long)hi << 32); for (uint32_t q = 0; q < k && q < 8; q++) { at(p + q) = (uint8_t)v; v >>= 8; } }
+    }
 };
 
-// flush [s, e) ring -> HBM: full 16-byte groups with vector stores, ragged ends bytewise (neighbours own the rest)
+// flush [s, e) ring -> HBM: full 16-byte groups with vector stores, the ragged head and tail (neighbours own the rest of those
+// groups) byte-parallel by lanes 0..15 / 16..31
 __device__ __forceinline__ void zk_ring_flush(const ZkRing& rg, uint32_t s, uint32_t e, int lane) {
     if (e <= s) return;
-    const uint32_t u0 = (s + rg.mis) >> 4, u1 = (e + rg.mis - 1) >> 4;     // 16-byte groups touched
-    for (uint32_t u = u0 + lane; u <= u1; u += 32) {
-        const uint32_t g = u << 4;                                        // shifted position of the group
-        const uint32_t lo = g > s + rg.mis ? g : s + rg.mis, hi = g + 16 < e + rg.mis ? g + 16 : e + rg.mis;
-        if (hi - lo == 16) *(uint4*)(rg.out + (g - rg.mis)) = *(const uint4*)(rg.ring + (g & rg.mask));
-        else for (uint32_t q = lo; q < hi; q++) rg.out[q - rg.mis] = rg.ring[q & rg.mask];
-    }
+    const uint32_t sb = s + rg.mis, eb = e + rg.mis;                       // shifted positions: 16-byte groups line up with HBM
+    const uint32_t uf0 = (sb + 15) >> 4, uf1 = eb >> 4;                    // full groups [uf0, uf1)
+    for (uint32_t u = uf0 + lane; u < uf1; u += 32) { const uint32_t g = u << 4; *(uint4*)(rg.out + (g - rg.mis)) = *(const uint4*)(rg.ring + (g & rg.mask)); }
+    const uint32_t head_end = (uf0 << 4) < eb ? (uf0 << 4) : eb;
+    if (lane < 16) { const uint32_t q = sb + (uint32_t)lane; if (q < head_end) rg.out[q - rg.mis] = rg.ring[q & rg.mask]; }
+    else if (uf1 >= uf0) { const uint32_t q = (uf1 << 4) + (uint32_t)lane - 16u; if (q < eb) rg.out[q - rg.mis] = rg.ring[q & rg.mask]; }
 }
 
 // reload [s, e) HBM -> ring (after a direct HBM-to-HBM block)
@@ -1241,6 +1268,376 @@ __device__ __forceinline__ void zk_exec_body(ZkD2Smem& sm, const ZkDecodeArgs& a
     }
 }
 
+// =============================================================================================
+// K-D2 (second generation): the same job with in-order bookkeeping only.
+//
+// Profiling the dataflow kernel above (profiles/ncu_summary_bench_r1.txt) showed about 3 500 warp instructions per
+// 32-sequence chunk at 15 warps per SM: it was bound by instruction issue, not by the dependency chain of a frame (a
+// frame whose every chunk waits for its predecessor would still finish in ~2 ms at ~1 000 cycles per chunk).  This
+// version keeps the shared-memory ring, the 32-sequence chunks dealt round-robin to the W warps of the CTA and the ring
+// discipline (start rule, near / far sources, direct path for oversized chunks), and replaces the per-sequence dataflow
+// (descriptor search, completion masks, pre-announcement) by ONE monotone counter:
+//   done_pos     every byte below it is final in the ring (or in HBM, for the direct path);  a match may go as soon as
+//                the part of its source that lies before its own chunk is below done_pos and the part inside its chunk
+//                is below the chunk's own frontier (the destination of its first pending match);
+//   the OLDEST unfinished chunk publishes its frontier after every round, so dependants in the next chunk start while it
+//   is still running; finished chunks are published in order by whoever polls (per-chunk flags, "helping").
+// About a fifth of the instructions per chunk, <= 64 registers, so 32 warps per SM stay resident.
+// =============================================================================================
+#define ZK_X2_META 64u
+#define ZK_X2_G 1u                       // items per group (one warp runs a group's items back to back: only group boundaries cost a cross-warp hand-off)
+struct ZkX2Smem {
+    unsigned long long ev_done, ev_flush;  // events (mbarriers): done_pos / done_chunk moved; flushed_pos / flushed_chunk moved
+    uint32_t done_pos, done_chunk;         // every byte below done_pos is final and readable; chunks [0, done_chunk) are done
+    uint32_t flushed_pos, flushed_chunk;   // ... and below flushed_pos it is in HBM too (ring slots may be reused)
+    int abort_code;
+    uint32_t end[ZK_X2_META], done[ZK_X2_META], flushed[ZK_X2_META];   // slot = chunk & 63; valid for chunk k iff tag == k + 1 (end: written before done)
+};
+#define ZK_X2_HINT_NS 20000u               // upper bound of one sleep (a missed wake-up costs at most this)
+
+__device__ __forceinline__ void zk_x2_abort(ZkX2Smem& sm, int code) {
+    atomicCAS(&sm.abort_code, 0, code);
+    __threadfence_block();
+    zk_event_signal(&sm.ev_done); zk_event_signal(&sm.ev_flush);
+}
+__device__ __forceinline__ bool zk_x2_aborted(ZkX2Smem& sm) { return __any_sync(0xFFFFFFFFu, *(volatile int*)&sm.abort_code != 0); }
+
+// advance the in-order prefixes as far as the per-chunk flags allow and wake the sleepers (called by whoever just set a flag)
+__device__ __noinline__ void zk_x2_advance_done(ZkX2Smem& sm) {
+    uint32_t dc = ZK_VOL(sm.done_chunk), dc0 = dc, dp = 0;
+    while (ZK_VOL(sm.done[dc & (ZK_X2_META - 1)]) == dc + 1) { dp = ZK_VOL(sm.end[dc & (ZK_X2_META - 1)]); dc++; }
+    if (dc != dc0) { atomicMax(&sm.done_pos, dp); __threadfence_block(); atomicMax(&sm.done_chunk, dc); __threadfence_block(); zk_event_signal(&sm.ev_done); }
+}
+__device__ __noinline__ void zk_x2_advance_flushed(ZkX2Smem& sm) {
+    uint32_t fc = ZK_VOL(sm.flushed_chunk), fc0 = fc, fp = 0;
+    while (ZK_VOL(sm.flushed[fc & (ZK_X2_META - 1)]) == fc + 1) { fp = ZK_VOL(sm.end[fc & (ZK_X2_META - 1)]); fc++; }
+    if (fc != fc0) { atomicMax(&sm.flushed_pos, fp); __threadfence_block(); atomicMax(&sm.flushed_chunk, fc); __threadfence_block(); zk_event_signal(&sm.ev_flush); }
+}
+
+// warp-uniform wait until an item of group g (ending at end_pos) may start; false if the CTA aborted.
+// exclusive: every earlier group is done and flushed (the item then runs alone, HBM to HBM; earlier items of the same group
+// were flushed by this very warp).
+__device__ __forceinline__ bool zk_x2_wait_start(ZkX2Smem& sm, uint32_t g, uint32_t end_pos, uint32_t window, bool exclusive, int lane) {
+    uint32_t ok = 0;
+    if (lane == 0) {
+        uint32_t ph = 2;                                                     // parity not known yet
+        for (;;) {
+            const uint32_t fg = ZK_VOL(sm.flushed_chunk), fp = ZK_VOL(sm.flushed_pos);
+            if (exclusive ? (fg == g) : (fg == g || (end_pos - fp <= window && g - fg < ZK_X2_META - 2))) { ok = 1; break; }
+            if (*(volatile int*)&sm.abort_code != 0) break;
+            if (ph == 2) { ph = zk_event_parity(&sm.ev_flush); continue; }   // learn the phase, then look again before sleeping
+            if (zk_event_sleep(&sm.ev_flush, ph, ZK_X2_HINT_NS)) ph ^= 1;
+        }
+    }
+    return __shfl_sync(0xFFFFFFFFu, ok, 0) != 0;
+}
+// lane 0: sleep until done_pos >= want (returns the value seen) or the CTA aborts (returns 0xFFFFFFFF)
+__device__ __forceinline__ uint32_t zk_x2_wait_done_pos(ZkX2Smem& sm, uint32_t want) {
+    uint32_t ph = 2;
+    for (;;) {
+        const uint32_t dp = ZK_VOL(sm.done_pos);
+        if (dp >= want) return dp;
+        if (*(volatile int*)&sm.abort_code != 0) return 0xFFFFFFFFu;
+        if (ph == 2) { ph = zk_event_parity(&sm.ev_done); continue; }
+        if (zk_event_sleep(&sm.ev_done, ph, ZK_X2_HINT_NS)) ph ^= 1;
+    }
+}
+// an item of group g, ending at end_pos, is final in the ring (or in HBM).  The last item of a group publishes the group;
+// before that, the OLDEST group publishes its progress item by item (dependants need not wait for the whole group).
+__device__ __forceinline__ void zk_x2_item_done(ZkX2Smem& sm, uint32_t g, uint32_t end_pos, bool last, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        if (last) { ZK_VOL(sm.end[g & (ZK_X2_META - 1)]) = end_pos; __threadfence_block(); ZK_VOL(sm.done[g & (ZK_X2_META - 1)]) = g + 1; __threadfence_block(); zk_x2_advance_done(sm); }
+        else if (ZK_VOL(sm.done_chunk) == g && end_pos > ZK_VOL(sm.done_pos)) { atomicMax(&sm.done_pos, end_pos); __threadfence_block(); zk_event_signal(&sm.ev_done); }
+    }
+}
+__device__ __forceinline__ void zk_x2_item_flushed(ZkX2Smem& sm, uint32_t g, uint32_t end_pos, bool last, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        if (last) { ZK_VOL(sm.flushed[g & (ZK_X2_META - 1)]) = g + 1; __threadfence_block(); zk_x2_advance_flushed(sm); }
+        else if (ZK_VOL(sm.flushed_chunk) == g && end_pos > ZK_VOL(sm.flushed_pos)) { atomicMax(&sm.flushed_pos, end_pos); __threadfence_block(); zk_event_signal(&sm.ev_flush); }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void zk_exec2_body(ZkX2Smem& sm, const ZkDecodeArgs& a, uint32_t ring_bytes) {
+    ZK_DYN_SMEM(ring_mem);
+    const uint32_t e = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    ZkEntry ent = a.entries[e];
+    if (ent.status != 0 || a.counters->overflow) return;
+    if (threadIdx.x == 0) { sm.done_pos = 0; sm.done_chunk = 0; sm.flushed_pos = 0; sm.flushed_chunk = 0; sm.abort_code = 0; zk_event_init(&sm.ev_done); zk_event_init(&sm.ev_flush); }
+    for (uint32_t i = threadIdx.x; i < ZK_X2_META; i += blockDim.x) { sm.done[i] = 0; sm.flushed[i] = 0; sm.end[i] = 0; }
+    __syncthreads();
+    uint8_t* out = a.dst + a.d_off[e];
+    const unsigned long long cap64 = a.d_off[e + 1] - a.d_off[e];
+    const uint32_t cap = cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cap64;
+    const uint8_t* ebase = a.comp + a.c_off[e];
+    ZkRing rg; rg.ring = ring_mem; rg.mask = ring_bytes - 1; rg.mis = (uint32_t)((uintptr_t)out & 15); rg.out = out;
+    const uint32_t half = ring_bytes >> 1;
+
+    uint32_t pos = 0, zstart = 0, chunk_base = 0, gstart = 0;
+    uint32_t R0 = 1, R1 = 4, R2 = 8;
+    const uint32_t need = a.d_need ? a.d_need[e] : 0xFFFFFFFFu;      // range reads: stop at the first block boundary at or after the wanted prefix
+    bool stopped = false;
+    for (uint32_t bi = 0; bi < ent.n_blocks; bi++) {
+        if (zk_x2_aborted(sm)) break;
+        if (pos >= need) { stopped = true; break; }
+        const uint32_t bidx = ent.first_block + bi;
+        const ZkBlock blk = a.blocks[bidx];
+        if (blk.flags & ZKB_FIRST) { R0 = 1; R1 = 4; R2 = 8; zstart = pos; }
+        if (blk.status != 0 || blk.lit_status != 0) { zk_x2_abort(sm, blk.status ? -blk.status : -blk.lit_status); break; }
+        const bool has_seq = blk.type == 2 && blk.nseq > 0;
+        const uint32_t nchunks = has_seq ? (blk.nseq + 31) / 32 + 1 : 1;
+        if ((unsigned long long)pos + blk.regen > cap) { zk_x2_abort(sm, ZKZ_DST_TOO_SMALL); break; }
+        // items (32-sequence chunks, trailing literals, whole non-sequence blocks) are numbered through the entry; ZK_X2_G
+        // consecutive items form a group, group g belongs to warp g % W, which runs its items one after the other
+        const uint32_t g_lo = chunk_base / ZK_X2_G;
+        for (uint32_t g = g_lo + ((uint32_t)warp + (uint32_t)W - g_lo % (uint32_t)W) % (uint32_t)W; g * ZK_X2_G < chunk_base + nchunks; g += (uint32_t)W)
+        for (uint32_t c = g * ZK_X2_G > chunk_base ? g * ZK_X2_G : chunk_base; c < (g + 1) * ZK_X2_G && c < chunk_base + nchunks; c++) {
+            const uint32_t j = c - chunk_base;
+            const bool glast = (c + 1) % ZK_X2_G == 0;                       // (the entry's last, incomplete group is closed after the loop)
+            if (!has_seq) {
+                // ---------------- Raw block / RLE block / literals-only compressed block: direct path, runs alone
+                if (c % ZK_X2_G == 0) gstart = pos;
+                if (!zk_x2_wait_start(sm, g, pos + blk.regen, 0, true, lane)) break;
+                if (blk.type == 0) zk_warp_copy(out + pos, ebase + blk.src, blk.size, lane);
+                else if (blk.type == 1) zk_warp_fill(out + pos, ebase[blk.src], blk.size, lane);
+                else if (blk.lit_kind == 1) zk_warp_fill(out + pos, blk.lit_byte, blk.lit_size, lane);
+                else zk_warp_copy(out + pos, blk.lit_kind == 0 ? ebase + blk.lit_src : a.lit + blk.lit_base, blk.lit_size, lane);
+                __syncwarp();
+                { uint32_t en = pos + blk.regen; zk_ring_reload(rg, en > half ? en - half : 0, en, lane, 32); }
+                zk_x2_item_done(sm, g, pos + blk.regen, glast, lane);
+                zk_x2_item_flushed(sm, g, pos + blk.regen, glast, lane);
+                continue;
+            }
+            const uint32_t* s_lit = a.seq_lit_end + blk.seq_base;
+            const uint32_t* s_out = a.seq_out_end + blk.seq_base;
+            const uint8_t* lit = blk.lit_kind == 0 ? ebase + blk.lit_src : a.lit + blk.lit_base;
+            if (j == nchunks - 1) {
+                // ---------------- trailing literals of the block
+                const uint32_t le = s_lit[blk.nseq - 1], oe = s_out[blk.nseq - 1];
+                const uint32_t n = blk.lit_size - le, st0 = pos + oe, en = pos + blk.regen;
+                const bool direct = n > half;
+                if (c % ZK_X2_G == 0) gstart = st0;
+                if (!zk_x2_wait_start(sm, g, en, half, direct, lane)) break;
+                if (direct) {
+                    if (blk.lit_kind == 1) zk_warp_fill(out + st0, blk.lit_byte, n, lane);
+                    else zk_warp_copy(out + st0, lit + le, n, lane);
+                    __syncwarp();
+                    zk_ring_reload(rg, en - half, en, lane, 32);
+                    zk_x2_item_done(sm, g, en, glast, lane);
+                } else {
+                    for (uint32_t i = lane; i < n; i += 32) rg.at(st0 + i) = blk.lit_kind == 1 ? blk.lit_byte : lit[le + i];
+                    zk_x2_item_done(sm, g, en, glast, lane);
+                    __syncwarp();
+                    zk_ring_flush(rg, st0, en, lane);
+                }
+                zk_x2_item_flushed(sm, g, en, glast, lane);
+                continue;
+            }
+            // ---------------- 32 sequences, one per lane (all loads issued before the first use)
+            const uint32_t s = j * 32 + lane;
+            const bool valid = s < blk.nseq;
+            const uint32_t sc = valid ? s : blk.nseq - 1;      // lanes past the last sequence repeat its cumulative ends (zero-length runs)
+            const uint32_t le = s_lit[sc], oe = s_out[sc];
+            const uint32_t offv = valid ? a.seq_off[blk.seq_base + s] : 0u;
+            uint32_t le_first = 0, oe_first = 0;
+            if (lane == 0 && s) { le_first = s_lit[s - 1]; oe_first = s_out[s - 1]; }
+            uint32_t le_prev = __shfl_up_sync(0xFFFFFFFFu, le, 1), oe_prev = __shfl_up_sync(0xFFFFFFFFu, oe, 1);
+            if (lane == 0) { le_prev = le_first; oe_prev = oe_first; }
+            const uint32_t ll = le - le_prev, ml = (oe - oe_prev) - ll;
+            const uint32_t o_lit = pos + oe_prev, md = o_lit + ll;          // entry-relative positions
+            uint32_t off = offv;
+            bool bad = false;
+            if (valid) {
+                if (offv & ZK_SYM) {
+                    const uint32_t sl = ZK_SYM_SLOT(offv), dl = ZK_SYM_DELTA(offv);
+                    const uint32_t r = sl == 0 ? R0 : (sl == 1 ? R1 : R2);
+                    bad = r <= dl; off = r - dl;
+                }
+                if (off == 0 || off > md - zstart) bad = true;
+            }
+            if (__any_sync(0xFFFFFFFFu, bad)) { zk_x2_abort(sm, ZKZ_CORRUPTION); break; }
+            const uint32_t chunk_start = pos + __shfl_sync(0xFFFFFFFFu, oe_prev, 0);
+            const uint32_t chunk_end = pos + __shfl_sync(0xFFFFFFFFu, oe, 31);
+            const bool direct = chunk_end - chunk_start > half;
+            if (c % ZK_X2_G == 0) gstart = chunk_start;
+            if (!glast && j + 2 < nchunks) {      // the next item is this warp's too: pull its sequences and the start of its literals towards L1
+                const uint32_t le_last = __shfl_sync(0xFFFFFFFFu, le, 31);
+                if (lane == 0) { zk_prefetch_l1(s_lit + s + 32); zk_prefetch_l1(s_out + s + 32); zk_prefetch_l1(a.seq_off + blk.seq_base + s + 32); }
+                if (lane >= 4 && lane < 8 && blk.lit_kind != 1) zk_prefetch_l1(lit + le_last + (uint32_t)(lane - 4) * 64u);
+            }
+            if (!zk_x2_wait_start(sm, g, chunk_end, half, direct, lane)) break;
+
+            if (direct) {
+                // ======== huge chunk: HBM -> HBM, alone in flight (it is the oldest chunk and everything before it is flushed)
+                {
+                    uint32_t longlit = __ballot_sync(0xFFFFFFFFu, valid && ll >= 256);
+                    if (!longlit) zk_chunk_literals<false>(rg, lit, blk.lit_kind, blk.lit_byte, le, le_prev, o_lit, lane);
+                    else {
+                        if (valid && ll < 256) {
+                            uint8_t* d = out + o_lit;
+                            if (blk.lit_kind == 1) for (uint32_t i = 0; i < ll; i++) d[i] = blk.lit_byte;
+                            else { const uint8_t* sp = lit + le_prev; for (uint32_t i = 0; i < ll; i++) d[i] = sp[i]; }
+                        }
+                        while (longlit) {
+                            const int l = __ffs((int)longlit) - 1; longlit &= longlit - 1;
+                            const uint32_t n = __shfl_sync(0xFFFFFFFFu, ll, l), d = __shfl_sync(0xFFFFFFFFu, o_lit, l), sp = __shfl_sync(0xFFFFFFFFu, le_prev, l);
+                            if (blk.lit_kind == 1) zk_warp_fill(out + d, blk.lit_byte, n, lane);
+                            else zk_warp_copy(out + d, lit + sp, n, lane);
+                        }
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+                const uint32_t need_end = md - off + (ml < off ? ml : off);
+                uint32_t pending = __ballot_sync(0xFFFFFFFFu, valid && ml > 0);
+                while (pending) {
+                    const int first = __ffs((int)pending) - 1;
+                    const uint32_t frontier = __shfl_sync(0xFFFFFFFFu, md, first);
+                    const bool mine = (pending >> lane) & 1;
+                    const bool ready = mine && (need_end <= frontier || lane == first);
+                    const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, ready);
+                    if (ready && ml < ZK_LONG) {
+                        uint8_t* d = out + md; const uint8_t* sp = d - off;
+                        for (uint32_t i = 0; i < ml; i++) d[i] = sp[i];
+                    }
+                    uint32_t longm = __ballot_sync(0xFFFFFFFFu, ready && ml >= ZK_LONG);
+                    while (longm) {
+                        const int l = __ffs((int)longm) - 1; longm &= longm - 1;
+                        const uint32_t n = __shfl_sync(0xFFFFFFFFu, ml, l), d = __shfl_sync(0xFFFFFFFFu, md, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
+                        zk_warp_match(out + d, o, n, lane);
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    pending &= ~rmask;
+                }
+                zk_ring_reload(rg, chunk_end - half, chunk_end, lane, 32);
+                zk_x2_item_done(sm, g, chunk_end, glast, lane);
+                zk_x2_item_flushed(sm, g, chunk_end, glast, lane);
+                continue;
+            }
+
+            // ======== normal chunk: build the output in the ring, then flush
+            zk_chunk_literals<true>(rg, lit, blk.lit_kind, blk.lit_byte, le, le_prev, o_lit, lane);      // no dependencies
+            // matches.  near: the source is still resident in the ring (distance < R/2 from the chunk start); far: it is in HBM
+            // (flushed, by the start rule) and has no dependency on anything in flight.
+            const uint32_t src0 = md - off;
+            const bool has_m = valid && ml > 0;
+            const bool near_src = src0 + half >= chunk_start;
+            const uint32_t need_end = src0 + (ml < off ? ml : off);
+            const bool ext_dep = near_src && src0 < gstart;                            // part of the source was produced by OTHER warps' groups
+            const uint32_t ext_need = need_end < gstart ? need_end : gstart;           // (earlier items of this group are final: program order)
+            bool aborted = false;
+            // ---- far matches first: nothing to wait for.  Short ones lane by lane with all the loads of up to 16 bytes in flight at
+            // once (one round trip for most matches), long ones by the whole warp.
+            {
+                const bool far_m = has_m && !near_src;
+                if (far_m && ml < ZK_LONG) {
+                    const uint8_t* sp = out + src0;
+                    for (uint32_t i = 0; i < ml; i += 16) {
+                        const unsigned long long v0 = zk_ld8_unaligned(sp + i), v1 = ml - i > 8 ? zk_ld8_unaligned(sp + i + 8) : 0ull;
+                        rg.st8(md + i, (uint32_t)v0, (uint32_t)(v0 >> 32), ml - i);
+                        if (ml - i > 8) rg.st8(md + i + 8, (uint32_t)v1, (uint32_t)(v1 >> 32), ml - i - 8);
+                    }
+                }
+                uint32_t longf = __ballot_sync(0xFFFFFFFFu, far_m && ml >= ZK_LONG);
+                while (longf) {
+                    const int l = __ffs((int)longf) - 1; longf &= longf - 1;
+                    const uint32_t n = __shfl_sync(0xFFFFFFFFu, ml, l), d = __shfl_sync(0xFFFFFFFFu, md, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
+                    const uint8_t* sp = out + (d - o);
+                    for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = sp[i];
+                }
+            }
+            uint32_t pending = __ballot_sync(0xFFFFFFFFu, has_m && near_src);
+            __threadfence_block();
+            __syncwarp();                                                              // literals and far matches are visible to every lane
+            uint32_t dp = __shfl_sync(0xFFFFFFFFu, ZK_VOL(sm.done_pos), 0);          // one reading for the whole warp (the branches below must be uniform)
+            while (pending) {
+                const int first = __ffs((int)pending) - 1;
+                const uint32_t frontier = __shfl_sync(0xFFFFFFFFu, md, first);       // inside this chunk everything below it is final
+                const bool mine = (pending >> lane) & 1;
+                const bool int_ok = mine && need_end <= frontier;                      // (always true for the first pending lane)
+                // the smallest done_pos that lets some lane go; sleep until it is reached (one lane sleeps, the warp issues nothing)
+                const uint32_t want = __reduce_min_sync(0xFFFFFFFFu, int_ok ? (ext_dep ? ext_need : 0u) : 0xFFFFFFFFu);
+                if (want > dp) {
+                    uint32_t v = 0;
+                    if (lane == 0) v = zk_x2_wait_done_pos(sm, want);
+                    dp = __shfl_sync(0xFFFFFFFFu, v, 0);
+                    if (dp == 0xFFFFFFFFu) { aborted = true; break; }
+                    __threadfence_block();         // acquire: done_pos was read before the data is
+                }
+                const bool ready = int_ok && (!ext_dep || ext_need <= dp);
+                const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, ready);
+                if (ready && ml < ZK_LONG) rg.copy_near(md, src0, ml);
+                uint32_t longm = __ballot_sync(0xFFFFFFFFu, ready && ml >= ZK_LONG);
+                while (longm) {
+                    const int l = __ffs((int)longm) - 1; longm &= longm - 1;
+                    const uint32_t n = __shfl_sync(0xFFFFFFFFu, ml, l), d = __shfl_sync(0xFFFFFFFFu, md, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
+                    if (o >= n) { for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = rg.at(d - o + i); }
+                    else if (o >= 32) {           // overlapping, period >= 32: 32 bytes per step are already final
+                        for (uint32_t i0 = 0; i0 < n; i0 += 32) { const uint32_t i = i0 + lane; if (i < n) rg.at(d + i) = rg.at(d - o + i); __syncwarp(); }
+                    } else {                      // short period: replicate the pattern
+                        for (uint32_t i = lane; i < n; i += 32) rg.at(d + i) = rg.at(d - o + (i % o));
+                    }
+                }
+                pending &= ~rmask;
+                __threadfence_block();
+                __syncwarp();
+                // the oldest unfinished chunk publishes its frontier: dependants in later chunks need not wait for the whole chunk
+                if (pending) {
+                    const uint32_t nf = __shfl_sync(0xFFFFFFFFu, md, __ffs((int)pending) - 1);
+                    if (lane == 0 && ZK_VOL(sm.done_chunk) == g && nf > ZK_VOL(sm.done_pos)) {
+                        atomicMax(&sm.done_pos, nf); __threadfence_block(); zk_event_signal(&sm.ev_done);
+                    }
+                }
+            }
+            if (aborted) break;
+            zk_x2_item_done(sm, g, chunk_end, glast, lane);        // dependants can read the ring now ...
+            __syncwarp();
+            zk_ring_flush(rg, chunk_start, chunk_end, lane);       // ... while the HBM flush happens off the critical chain
+            zk_x2_item_flushed(sm, g, chunk_end, glast, lane);
+        }
+        // advance to the next block
+        if (has_seq) {
+            uint32_t v[3] = { blk.rep_out[0], blk.rep_out[1], blk.rep_out[2] }, n[3];
+            for (int q = 0; q < 3; q++) {
+                if (v[q] & ZK_SYM) { const uint32_t sl = ZK_SYM_SLOT(v[q]); const uint32_t r = sl == 0 ? R0 : (sl == 1 ? R1 : R2); n[q] = r - ZK_SYM_DELTA(v[q]); }
+                else n[q] = v[q];
+            }
+            R0 = n[0]; R1 = n[1]; R2 = n[2];
+        }
+        pos += blk.regen;
+        chunk_base += nchunks;
+        if (blk.flags & ZKB_LAST) {
+            if ((blk.flags & ZKB_HAS_FCS) && blk.fcs != (unsigned long long)(pos - zstart)) { zk_x2_abort(sm, ZKZ_CORRUPTION); break; }
+            if (threadIdx.x == 0) { a.blocks[bidx].hash_start = zstart; a.blocks[bidx].hash_len = pos - zstart; }
+        }
+    }
+    if (chunk_base % ZK_X2_G && (chunk_base / ZK_X2_G) % (uint32_t)W == (uint32_t)warp && !zk_x2_aborted(sm)) {
+        // the entry's last group has fewer than ZK_X2_G items: its owner closes it (nobody waits on it any more, but the
+        // in-order prefixes stay exact)
+        zk_x2_item_done(sm, chunk_base / ZK_X2_G, pos, true, lane);
+        zk_x2_item_flushed(sm, chunk_base / ZK_X2_G, pos, true, lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int code = sm.abort_code;
+        if (!code && !stopped && (unsigned long long)pos != cap64) code = pos < cap64 ? ZKZ_SRC_SIZE_WRONG : ZKZ_DST_TOO_SMALL;
+        a.entries[e].status = code ? -code : 0;
+        a.entries[e].produced = pos;
+        if (code) atomicAdd(&a.counters->n_errors, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) zk_exec2_kernel(ZkDecodeArgs a, uint32_t ring_bytes) {
+    __shared__ ZkX2Smem sm;
+    zk_exec2_body(sm, a, ring_bytes);
+}
+
 // Two register budgets for the same body: up to 16 warps per entry (<= 128 registers, few entries per SM), and a
 // 5-warp variant compiled for 4 CTAs per SM (<= 102 registers) for large batches, where every entry of the batch should
 // stay resident and the warps per SM are what hides the latency.
@@ -1256,54 +1653,6 @@ __global__ void __launch_bounds__(160, 4) zk_exec_kernel_w5(ZkDecodeArgs a, uint
 // =============================================================================================
 // K-D3: XXH64 content checksum (A.8), one warp per entry, lanes 0..3 carry the four accumulators
 // =============================================================================================
-#define ZK_P1 0x9E3779B185EBCA87ull
-#define ZK_P2 0xC2B2AE3D27D4EB4Full
-#define ZK_P3 0x165667B19E3779F9ull
-#define ZK_P4 0x85EBCA77C2B2AE63ull
-#define ZK_P5 0x27D4EB2F165667C5ull
-__device__ __forceinline__ unsigned long long zk_rotl64(unsigned long long x, int r) { return (x << r) | (x >> (64 - r)); }
-__device__ __forceinline__ unsigned long long zk_xx_round(unsigned long long acc, unsigned long long in) { return zk_rotl64(acc + in * ZK_P2, 31) * ZK_P1; }
-__device__ __forceinline__ unsigned long long zk_xx_merge(unsigned long long h, unsigned long long v) { return (h ^ zk_xx_round(0, v)) * ZK_P1 + ZK_P4; }
-__device__ __forceinline__ unsigned long long zk_ld_u64_unaligned(const uint8_t* p) {
-    uintptr_t a = (uintptr_t)p; uint32_t mis = (uint32_t)(a & 7);
-    const unsigned long long* q = (const unsigned long long*)(a - mis);
-    if (mis == 0) return q[0];
-    return (q[0] >> (mis * 8)) | (q[1] << (64 - mis * 8));
-}
-
-// whole-warp XXH64 of p[0..len); result valid in every lane
-__device__ unsigned long long zk_warp_xxh64(const uint8_t* p, uint32_t len, int lane) {
-    unsigned long long h;
-    uint32_t done = 0;
-    if (len >= 32) {
-        unsigned long long acc = lane == 0 ? ZK_P1 + ZK_P2 : (lane == 1 ? ZK_P2 : (lane == 2 ? 0ull : 0ull - ZK_P1));
-        uint32_t stripes = len / 32;
-        if (lane < 4) {
-            const uint8_t* q = p + lane * 8;
-            uint32_t i = 0;
-            for (; i + 4 <= stripes; i += 4) {          // 4 loads in flight per lane
-                unsigned long long w0 = zk_ld_u64_unaligned(q), w1 = zk_ld_u64_unaligned(q + 32),
-                                   w2 = zk_ld_u64_unaligned(q + 64), w3 = zk_ld_u64_unaligned(q + 96);
-                acc = zk_xx_round(acc, w0); acc = zk_xx_round(acc, w1); acc = zk_xx_round(acc, w2); acc = zk_xx_round(acc, w3);
-                q += 128;
-            }
-            for (; i < stripes; i++) { acc = zk_xx_round(acc, zk_ld_u64_unaligned(q)); q += 32; }
-        }
-        unsigned long long v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1),
-                           v3 = __shfl_sync(0xFFFFFFFFu, acc, 2), v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
-        h = zk_rotl64(v1, 1) + zk_rotl64(v2, 7) + zk_rotl64(v3, 12) + zk_rotl64(v4, 18);
-        h = zk_xx_merge(h, v1); h = zk_xx_merge(h, v2); h = zk_xx_merge(h, v3); h = zk_xx_merge(h, v4);
-        done = stripes * 32;
-    } else h = ZK_P5;
-    h += (unsigned long long)len;
-    const uint8_t* q = p + done; uint32_t rem = len - done;
-    while (rem >= 8) { h ^= zk_xx_round(0, zk_ld_u64_unaligned(q)); h = zk_rotl64(h, 27) * ZK_P1 + ZK_P4; q += 8; rem -= 8; }
-    if (rem >= 4) { h ^= (unsigned long long)zk_ld_le32(q) * ZK_P1; h = zk_rotl64(h, 23) * ZK_P2 + ZK_P3; q += 4; rem -= 4; }
-    while (rem) { h ^= (unsigned long long)(*q) * ZK_P5; h = zk_rotl64(h, 11) * ZK_P1; q++; rem--; }
-    h ^= h >> 33; h *= ZK_P2; h ^= h >> 29; h *= ZK_P3; h ^= h >> 32;
-    return h;
-}
-
 __global__ void __launch_bounds__(128) zk_xxh64_kernel(ZkDecodeArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1457,6 +1806,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem + 65536));
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec_kernel_w5, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        ZK_CUDA_OK(cudaFuncSetAttribute(zk_exec2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         ws->attr_set = true;
     }
     uint32_t gs = (uint32_t)sms * ws->seq_ctas, gh = (uint32_t)sms * ws->huf_ctas;          // persistent CTAs: as many as fit (shared memory: 4 x 51 KiB, 5 x 41 KiB)
@@ -1488,21 +1838,35 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     // CTA and ring size such that (if possible) every entry of the batch is resident at once.
     // (`share` > 1: that many sub-batches of a host pipeline run concurrently on different streams)
     int per_sm = (int)(((unsigned long long)n * (unsigned)(ws->share > 0 ? ws->share : 1) + (uint32_t)sms - 1) / (uint32_t)sms);
+    if (per_sm < 1) per_sm = 1;
     int W = exec_warps;
-    // 126 registers/thread -> 16 warps per SM; from four entries per SM on, the 96-register build of the same body
-    // (20 warps per SM, <= 5 per entry) keeps every entry of the batch resident with one more warp each
-    bool small_regs = false;
-    if (W <= 0) {
-        if (per_sm >= 4) { W = 20 / per_sm; if (W < 2) W = 2; small_regs = true; }
-        else W = 16 / per_sm;
-    } else small_regs = W <= 5 && per_sm >= 4;
-    if (W > 16) W = 16;
-    uint32_t ring = 128 * 1024;
-    while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;
-    if (ws->ring_override) ring = ws->ring_override;
     ws->prof.begin(3, stream);
-    if (small_regs) ZK_LAUNCH(zk_exec_kernel_w5, n, W * 32, ring, stream, a, ring);
-    else ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
+    if (!ws->exec_v1) {
+        // second-generation kernel: <= 64 registers, so 32 warps per SM whatever the split; ring = what is left of the
+        // SM's shared memory per resident entry
+        if (per_sm > 8) per_sm = 8;
+        if (W <= 0) W = 32 / per_sm;
+        if (W > 32) W = 32;
+        if (W < 2) W = 2;
+        uint32_t ring = 128 * 1024;
+        while (ring > 8 * 1024 && ((size_t)ring + 2048) * (size_t)per_sm > 220 * 1024) ring >>= 1;
+        if (ws->ring_override) ring = ws->ring_override;
+        ZK_LAUNCH(zk_exec2_kernel, n, W * 32, ring, stream, a, ring);
+    } else {
+        // 126 registers/thread -> 16 warps per SM; from four entries per SM on, the 96-register build of the same body
+        // (20 warps per SM, <= 5 per entry) keeps every entry of the batch resident with one more warp each
+        bool small_regs = false;
+        if (W <= 0) {
+            if (per_sm >= 4) { W = 20 / per_sm; if (W < 2) W = 2; small_regs = true; }
+            else W = 16 / per_sm;
+        } else small_regs = W <= 5 && per_sm >= 4;
+        if (W > 16) W = 16;
+        uint32_t ring = 128 * 1024;
+        while (ring > 8 * 1024 && (size_t)ring * (size_t)per_sm > 200 * 1024) ring >>= 1;
+        if (ws->ring_override) ring = ws->ring_override;
+        if (small_regs) ZK_LAUNCH(zk_exec_kernel_w5, n, W * 32, ring, stream, a, ring);
+        else ZK_LAUNCH(zk_exec_kernel, n, W * 32, ring, stream, a, ring);
+    }
     ws->prof.end(3, stream);
     if (verify_checksum) { ws->prof.begin(4, stream); ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a); ws->prof.end(4, stream); }
     ZK_CUDA_OK(cudaMemcpyAsync(ws->h_entries, ws->entries, (size_t)n * sizeof(ZkEntry), cudaMemcpyDeviceToHost, stream));

@@ -28,6 +28,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint32_t* d_need = nullptr; uint32_t* h_need = nullptr;
     uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
     bool attr_set = false; uint32_t ring_override = 0;
+    bool exec_v1 = false;             // ZK_EXEC_V1=1: the first-generation (dataflow) exec kernel, kept for A/B measurements
     uint32_t huf_pad = 0;             // extra dynamic smem per Huffman CTA: fewer resident CTAs -> more L1 for the streams (tuning)
     unsigned long long* trace = nullptr;
     int share = 1;                    // how many batches share the GPU concurrently (host pipeline depth)

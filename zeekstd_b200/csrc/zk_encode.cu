@@ -991,22 +991,7 @@ __global__ void __launch_bounds__(128) zk_block_finish_kernel(ZkEncodeArgs a) {
 // =============================================================================================
 // K-C3: frame layout + gather
 // =============================================================================================
-#define ZKC_P1 0x9E3779B185EBCA87ull
-#define ZKC_P2 0xC2B2AE3D27D4EB4Full
-#define ZKC_P3 0x165667B19E3779F9ull
-#define ZKC_P4 0x85EBCA77C2B2AE63ull
-#define ZKC_P5 0x27D4EB2F165667C5ull
-__device__ __forceinline__ unsigned long long zkc_rotl64(unsigned long long x, int r) { return (x << r) | (x >> (64 - r)); }
-__device__ __forceinline__ unsigned long long zkc_round(unsigned long long acc, unsigned long long in) { return zkc_rotl64(acc + in * ZKC_P2, 31) * ZKC_P1; }
-__device__ __forceinline__ unsigned long long zkc_merge(unsigned long long h, unsigned long long v) { return (h ^ zkc_round(0, v)) * ZKC_P1 + ZKC_P4; }
-__device__ __forceinline__ unsigned long long zkc_ld_u64(const uint8_t* p) {
-    uintptr_t a = (uintptr_t)p; uint32_t mis = (uint32_t)(a & 7);
-    const unsigned long long* q = (const unsigned long long*)(a - mis);
-    if (mis == 0) return q[0];
-    return (q[0] >> (mis * 8)) | (q[1] << (64 - mis * 8));
-}
-
-// XXH64 (A.8) of each frame's input, one warp per frame, lanes 0..3 carry the accumulators
+// XXH64 (A.8) of each frame's input, one warp per frame (zk_warp_xxh64: coalesced loads, products off the chain)
 __global__ void __launch_bounds__(128) zk_frame_hash_kernel(ZkEncodeArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1014,30 +999,7 @@ __global__ void __launch_bounds__(128) zk_frame_hash_kernel(ZkEncodeArgs a) {
     const size_t fstart = (size_t)f * a.frame_size;
     const size_t fend = fstart + a.frame_size < a.n ? fstart + a.frame_size : a.n;
     const uint8_t* p = a.src + fstart; const uint32_t len = (uint32_t)(fend - fstart);
-    unsigned long long h; uint32_t done = 0;
-    if (len >= 32) {
-        unsigned long long acc = lane == 0 ? ZKC_P1 + ZKC_P2 : (lane == 1 ? ZKC_P2 : (lane == 2 ? 0ull : 0ull - ZKC_P1));
-        const uint32_t stripes = len / 32;
-        if (lane < 4) {
-            const uint8_t* q = p + lane * 8; uint32_t i = 0;
-            for (; i + 4 <= stripes; i += 4) {
-                unsigned long long w0 = zkc_ld_u64(q), w1 = zkc_ld_u64(q + 32), w2 = zkc_ld_u64(q + 64), w3 = zkc_ld_u64(q + 96);
-                acc = zkc_round(acc, w0); acc = zkc_round(acc, w1); acc = zkc_round(acc, w2); acc = zkc_round(acc, w3);
-                q += 128;
-            }
-            for (; i < stripes; i++) { acc = zkc_round(acc, zkc_ld_u64(q)); q += 32; }
-        }
-        unsigned long long v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2), v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
-        h = zkc_rotl64(v1, 1) + zkc_rotl64(v2, 7) + zkc_rotl64(v3, 12) + zkc_rotl64(v4, 18);
-        h = zkc_merge(h, v1); h = zkc_merge(h, v2); h = zkc_merge(h, v3); h = zkc_merge(h, v4);
-        done = stripes * 32;
-    } else h = ZKC_P5;
-    h += (unsigned long long)len;
-    const uint8_t* q = p + done; uint32_t rem = len - done;
-    while (rem >= 8) { h ^= zkc_round(0, zkc_ld_u64(q)); h = zkc_rotl64(h, 27) * ZKC_P1 + ZKC_P4; q += 8; rem -= 8; }
-    if (rem >= 4) { h ^= (unsigned long long)zk_ld_le32(q) * ZKC_P1; h = zkc_rotl64(h, 23) * ZKC_P2 + ZKC_P3; q += 4; rem -= 4; }
-    while (rem) { h ^= (unsigned long long)(*q) * ZKC_P5; h = zkc_rotl64(h, 11) * ZKC_P1; q++; rem--; }
-    h ^= h >> 33; h *= ZKC_P2; h ^= h >> 29; h *= ZKC_P3; h ^= h >> 32;
+    const unsigned long long h = zk_warp_xxh64(p, len, lane);
     if (lane == 0) a.frame_hash[f] = (uint32_t)h;
 }
 
@@ -1139,6 +1101,7 @@ void zk_encode_ws_free(ZkEncodeWs* ws) {
     if (ws->side) cudaStreamDestroy(ws->side);
     if (ws->ev_a) cudaEventDestroy(ws->ev_a);
     if (ws->ev_b) cudaEventDestroy(ws->ev_b);
+    if (ws->ev_c) cudaEventDestroy(ws->ev_c);
     ws->prof.destroy();
     *ws = ZkEncodeWs();
 }
@@ -1191,6 +1154,22 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     a.frame_csize = (uint32_t*)(base + o_fcs); a.frame_off = (unsigned long long*)(base + o_foff); a.frame_hash = (uint32_t*)(base + o_fh);
     a.dst = d_dst; a.dst_cap = dst_cap; a.total = (unsigned long long*)(base + o_tot); a.error = (uint32_t*)(base + o_tot + 8);
     ZKC_CUDA_OK(cudaMemsetAsync(base + o_tot, 0, 16, stream));
+    // the content checksum only needs the input: it runs beside the match finder on the side stream (one warp per frame, bound
+    // by the latency of its four serial chains, so it leaves the machine to K-C1)
+    cudaStream_t ss = stream;
+    if (!ws->no_side) {
+        if (!ws->side) {
+            ZKC_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
+            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming));
+            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming));
+            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_c, cudaEventDisableTiming));
+        }
+        ss = ws->side;
+    }
+    if (checksum && ss != stream) {
+        ZKC_CUDA_OK(cudaEventRecord(ws->ev_c, stream)); ZKC_CUDA_OK(cudaStreamWaitEvent(ss, ws->ev_c, 0));     // after whatever produced the input
+        ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, ss, a);
+    }
     ws->prof.begin(5, stream);
     if (a.level <= 1) ZK_LAUNCH(zk_match_kernel<ZKC_HLOG_FAST>, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
     else ZK_LAUNCH(zk_match_kernel<ZKC_HLOG>, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
@@ -1198,15 +1177,6 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqWarp) * ZKC_SW;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
     // the two entropy kernels are independent and both latency-bound: run them side by side, join in zk_block_finish_kernel
-    cudaStream_t ss = stream;
-    if (!ws->no_side) {
-        if (!ws->side) {
-            ZKC_CUDA_OK(cudaStreamCreateWithPriority(&ws->side, cudaStreamNonBlocking, ws->prio));
-            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming));
-            ZKC_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming));
-        }
-        ss = ws->side;
-    }
     ws->prof.begin(6, stream);
     if (ss != stream) { ZKC_CUDA_OK(cudaEventRecord(ws->ev_a, stream)); ZKC_CUDA_OK(cudaStreamWaitEvent(ss, ws->ev_a, 0)); }
     ZK_LAUNCH(zk_seq_enc_kernel, (uint32_t)((n_blocks + ZKC_SW - 1) / ZKC_SW), 32 * ZKC_SW, seq_smem, ss, a);
@@ -1216,7 +1186,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ZK_LAUNCH(zk_block_finish_kernel, (uint32_t)((n_blocks + 3) / 4), 128, 0, stream, a);
     ws->prof.end(6, stream);
     ws->prof.begin(7, stream);
-    if (checksum) ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, stream, a);
+    if (checksum && ss == stream) ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, stream, a);   // else: already done on the side stream (joined by ev_b)
     ZK_LAUNCH(zk_frame_size_kernel, (n_frames + 255) / 256, 256, 0, stream, a);
     ZK_LAUNCH(zk_frame_scan_kernel, 1, 1024, 0, stream, a);
     ZK_LAUNCH(zk_frame_gather_kernel, (uint32_t)((n_blocks + 3) / 4), 128, 0, stream, a);

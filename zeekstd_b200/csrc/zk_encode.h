@@ -11,7 +11,7 @@ struct ZkEncodeWs {                    // HBM scratch owned by a zk_ctx slot, gr
     bool attr_set = false;
     int prio = 0;                     // CUDA stream priority of the side stream (matches the slot's stream)
     bool no_side = false;             // host pipelines: concurrency comes from the other sub-batches; every extra stream costs a hardware queue
-    cudaStream_t side = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // K-C2s runs beside K-C2l
+    cudaStream_t side = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;   // K-C2s runs beside K-C2l
     ZkProf prof;
 };
 

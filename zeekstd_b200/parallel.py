@@ -161,8 +161,19 @@ class Groups:
     directions of a step never queue behind each other (one NCCL communicator executes its operations in order)"""
 
     def __init__(self):
-        self.down = dist.new_group()
-        self.up = dist.new_group()
+        opts = None
+        if dist.get_backend() == "nccl":
+            # The exchange needs a small fraction of NVLink (16 GiB per ~0.3 s step); its kernels must not take SMs from the
+            # codec, whose frames want to be resident all at once: a few CTAs per NCCL kernel are plenty.
+            try:
+                import os
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(os.environ.get("ZK_NCCL_MAX_CTAS", "4"))
+                opts.config.min_ctas = 1
+            except Exception:
+                opts = None
+        self.down = dist.new_group(pg_options=opts) if opts is not None else dist.new_group()
+        self.up = dist.new_group(pg_options=opts) if opts is not None else dist.new_group()
 
 
 _groups: Groups | None = None
