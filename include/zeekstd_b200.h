@@ -104,6 +104,19 @@ int32_t zk_decompress_frames_upto(zk_ctx* ctx, const uint8_t* comp, const uint64
                                   uint32_t n_frames, uint8_t* dst, const uint32_t* d_need, int32_t verify_checksum, int32_t* status);
 
 /*
+ * Prefix / patch mode: the same calls with a raw-content prefix that precedes EVERY frame (the reference re-applies it per
+ * frame: cctx.ref_prefix at each frame start, encode.rs:332-338; dctx.ref_prefix before the first frame and after every frame
+ * end, decode.rs:211-214, 246-255).  Matches may reach back into the prefix; frames made this way only decode with the same
+ * prefix (libzstd: ZSTD_CCtx_refPrefix / ZSTD_DCtx_refPrefix).  prefix == NULL or prefix_len == 0: the plain calls.  HOST pointers.
+ */
+int32_t zk_compress_frames_prefix(zk_ctx* ctx, const uint8_t* src, size_t n, uint32_t frame_size, int32_t level,
+                                  int32_t checksum, const uint8_t* prefix, size_t prefix_len, uint8_t* dst, size_t dst_cap,
+                                  uint32_t* c_sizes, uint32_t* d_sizes, uint32_t frames_cap, uint32_t* n_frames, size_t* dst_len);
+int32_t zk_decompress_frames_prefix(zk_ctx* ctx, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off,
+                                    uint32_t n_frames, uint8_t* dst, const uint32_t* d_need, int32_t verify_checksum,
+                                    int32_t* status, const uint8_t* prefix, size_t prefix_len);
+
+/*
  * Device-resident variants (zero-copy; used for roofline measurements and multi-GPU pipelines).
  * d_* are CUDA device pointers, 16-byte aligned, with >= 16 readable bytes after the last byte;
  * offset / size arrays stay on the HOST.  cuda_stream is a cudaStream_t (NULL = the context's own
@@ -175,6 +188,11 @@ int32_t zk_encode_options_into_encoder(zk_encode_options* o, zk_write_fn write, 
 void zk_raw_encoder_free(zk_raw_encoder* e);
 int32_t zk_raw_encoder_compress(zk_raw_encoder* e, const uint8_t* input, size_t in_len, uint8_t* output,
                                 size_t out_len, zk_compression_progress* progress);     /* :398 / 311-354 */
+/* RawEncoder::compress_with_prefix: the prefix given at a frame's FIRST call is that frame's raw-content prefix (it must stay
+ * valid until the frame is closed -- 'b: 'a in the reference); NULL = none */
+int32_t zk_raw_encoder_compress_with_prefix(zk_raw_encoder* e, const uint8_t* input, size_t in_len, uint8_t* output,
+                                            size_t out_len, const uint8_t* prefix, size_t prefix_len,
+                                            zk_compression_progress* progress);            /* :311-354 */
 int32_t zk_raw_encoder_end_frame(zk_raw_encoder* e, uint8_t* output, size_t out_len,
                                  zk_epilogue_progress* progress);                       /* :438-472 */
 const zk_seek_table* zk_raw_encoder_seek_table(const zk_raw_encoder* e);               /* :479 */
@@ -184,6 +202,8 @@ void zk_raw_encoder_reset_seek_table(zk_raw_encoder* e);                        
 
 void zk_encoder_free(zk_encoder* e);
 int32_t zk_encoder_compress(zk_encoder* e, const uint8_t* buf, size_t len, size_t* consumed); /* :692 / 641-665 */
+int32_t zk_encoder_compress_with_prefix(zk_encoder* e, const uint8_t* buf, size_t len, const uint8_t* prefix,
+                                        size_t prefix_len, size_t* consumed);               /* :641-665 */
 int32_t zk_encoder_end_frame(zk_encoder* e, size_t* written);                          /* :704-717 */
 int32_t zk_encoder_flush(zk_encoder* e);                                                /* impl Write::flush :796 */
 /* finish()/finish_format() consume the encoder; *total = bytes written to the sink incl. seek table */
@@ -217,6 +237,9 @@ int32_t zk_decode_options_into_decoder(zk_decode_options* o, zk_decoder** out); 
 
 void zk_decoder_free(zk_decoder* d);
 int32_t zk_decoder_decompress(zk_decoder* d, uint8_t* buf, size_t len, size_t* produced); /* :314 / 201-270 */
+/* Decoder::decompress_with_prefix: every frame is decoded against the raw-content prefix (decode.rs:211-214, 246-255) */
+int32_t zk_decoder_decompress_with_prefix(zk_decoder* d, uint8_t* buf, size_t len, const uint8_t* prefix,
+                                          size_t prefix_len, size_t* produced);            /* :201-270 */
 void zk_decoder_reset(zk_decoder* d);                                                    /* :346-350 */
 int32_t zk_decoder_set_lower_frame(zk_decoder* d, uint32_t index, uint64_t* offset);    /* :367 */
 int32_t zk_decoder_set_upper_frame(zk_decoder* d, uint32_t index, uint64_t* offset);    /* :383 */

@@ -26,7 +26,7 @@ COVER_SEQ_BYTES = 48 << 20
 MATRIX_CELLS = ("n_raw", "n_rle", "n_comp", "lit_raw", "lit_rle", "lit_huf", "lit_treeless", "lit_1stream", "lit_4stream", "huf_direct", "huf_fse",
                 "mode_predef", "mode_rle", "mode_fse", "mode_repeat", "nseq0_blocks", "checksum_frames", "single_segment_frames",
                 "skippable_frames", "multi_frame_entries", "rep1", "rep2", "rep3", "rep1_minus_1", "rep_ll0", "overlap", "dict_id_rejected",
-                "frames_over_2MiB", "offsets_over_1MiB")
+                "frames_over_2MiB", "offsets_over_1MiB", "prefix_frames")
 
 
 def cover(entries, d_total: int | None = None, prefix=None):
@@ -431,6 +431,88 @@ def check_checksum_flag(ctx):
         st = zk.SeekTable.from_bytes(a, zk.Format.Foot, ctx.lib)
         for i in range(st.num_frames()):
             assert ((a[st.frame_start_comp(i) + 4] >> 2) & 1) == int(flag)
+
+
+def check_patch_cycle(ctx, policy=None):
+    """lib.rs:202-263 test_patch_cycle: a "binary patch" -- the new version compressed with the old one as raw-content prefix of
+    every frame, every stage in many small steps, decoded with the same prefix.  Plus what the reference cannot check: libzstd
+    (ZSTD_DCtx_refPrefix) restores our patch, and a patch written by libzstd (ZSTD_CCtx_refPrefix) decodes on our side."""
+    old = INPUT
+    new = INPUT + b"\nThe End"
+    opts = zk.EncodeOptions(ctx)
+    if policy:
+        opts.frame_size_policy(policy)
+    enc = opts.into_raw_encoder()
+    buf = bytearray(max(1, len(INPUT) // 500))
+    patch = bytearray()
+    pos = 0
+    while pos < len(new):
+        p = enc.compress_with_prefix(new[pos:], buf, old)
+        patch += buf[: p.out_progress]; pos += p.in_progress
+    while True:
+        p = enc.end_frame(buf)
+        patch += buf[: p.out_progress]
+        if p.data_left == 0:
+            break
+    ser = enc.into_seek_table().into_serializer()
+    while True:
+        n = ser.write_into(buf)
+        if n == 0:
+            break
+        patch += buf[:n]
+    patch = bytes(patch)
+    st = O.OracleSeekTable.parse(patch, "foot")
+    if policy is None:
+        assert len(patch) < len(new) // 20, len(patch)          # the point of a patch: almost everything comes from the prefix
+    # libzstd with the prefix restores it; without the prefix it cannot
+    out, sizes = O.ref_decompress_frames(patch[: st.c[-1]], st.c, st.d, prefix=old)
+    assert out.tobytes() == new
+    if policy is None:
+        _, sizes = O.ref_decompress_frames(patch[: st.c[-1]], st.c, st.d)
+        assert any(s < 0 for s in sizes)
+    dec = zk.Decoder(zk.DecodeOptions(patch, ctx))
+    got = bytearray()
+    while True:
+        n = dec.decompress_with_prefix(buf, old)
+        if n == 0:
+            break
+        got += buf[:n]
+    assert bytes(got) == new
+    # the other direction: the reference path writes the patch
+    for fs in (len(new), 4000):
+        frames, cs, ds = O.ref_compress_frames(np.frombuffer(new, dtype=np.uint8), fs, 3, True, prefix=old)
+        out, stt, rc = ctx.decompress_frames(np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8), offsets(cs), offsets(ds), True, prefix=old)
+        assert rc == 0 and out.tobytes() == new
+        cover(frames, len(new), prefix=old)
+        COVERAGE["prefix_frames"] = COVERAGE.get("prefix_frames", 0) + len(frames)
+
+
+def check_prefix_batches(ctx, n: int = 300_000, frame_size: int = 50_000):
+    """prefix mode of the batch codec on more than one frame and more than one block per frame: text whose vocabulary lives
+    in the prefix; both implementations, both directions, several prefix lengths (shorter and longer than the encoder's window)"""
+    text = np.frombuffer(golden_bytes("dickens_96k.txt"), dtype=np.uint8)
+    data = np.concatenate([text[10_000:60_000]] * (n // 50_000 + 1))[:n].copy()
+    data[::977] ^= 1                                                   # not an exact copy of the prefix
+    for plen in (1, 1000, 40_000, 98_304):
+        prefix = text[:plen]
+        comp, cs, ds = ctx.compress_frames(data, frame_size, 3, True, prefix=prefix)
+        out, sizes = O.ref_decompress_frames(comp, offsets(cs), offsets(ds), prefix=prefix)          # libzstd restores ours
+        assert sizes == [int(d) for d in ds] and out.tobytes() == data.tobytes(), plen
+        back, st, rc = ctx.decompress_frames(np.concatenate([comp, np.zeros(64, np.uint8)]), offsets(cs), offsets(ds), True, prefix=prefix)
+        assert rc == 0 and back.tobytes() == data.tobytes()
+        if plen >= 40_000:
+            plain = ctx.compress_frames(data, frame_size, 3, True)[0]
+            assert comp.size < plain.size, (plen, comp.size, plain.size)        # the prefix was found
+        frames, rcs, rds = O.ref_compress_frames(data, frame_size, 3, True, prefix=prefix)             # ours restores libzstd's
+        back, st, rc = ctx.decompress_frames(np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8), offsets(rcs), offsets(rds), True, prefix=prefix)
+        assert rc == 0 and back.tobytes() == data.tobytes(), plen
+        _, ss = O.oracle_decompress_ex(b"".join(frames), n + 1, prefix=prefix)
+        if plen >= 1000:
+            assert ss["prefix_matches"] > 0
+        COVERAGE["prefix_frames"] = COVERAGE.get("prefix_frames", 0) + len(frames)
+    # a wrong prefix must not decode silently (checksum on)
+    back, st, rc = ctx.decompress_frames(np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8), offsets(rcs), offsets(rds), True, prefix=text[:plen - 5])
+    assert rc != 0
 
 
 # ------------------------------------------------------------------------------------------------ API: decode side

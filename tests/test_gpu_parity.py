@@ -95,6 +95,17 @@ def test_special_entries(ctx):
     cases.check_special_entries(ctx)
 
 
+def test_patch_cycle(ctx):
+    """lib.rs:289-300 patch_cycle (+ the two frame-size-policy variants of lib.rs:302-313)"""
+    cases.check_patch_cycle(ctx)
+    cases.check_patch_cycle(ctx, zk.FrameSizePolicy.Uncompressed(3000))
+    cases.check_patch_cycle(ctx, zk.FrameSizePolicy.Compressed(700))
+
+
+def test_prefix_batches(ctx):
+    cases.check_prefix_batches(ctx)
+
+
 def test_level3_2mib_frames_checksum(ctx):
     """config-4 shape: level 3 (2 MiB window: offsets reach back to the frame start), 2 MiB frames, checksum on"""
     x = corpus.make_mix(24 << 20, seed=20260925, mix=corpus.CLASS_MIX_MIXED).numpy()

@@ -69,6 +69,17 @@ def test_special_entries(ctx):
     cases.check_special_entries(ctx)
 
 
+def test_patch_cycle(ctx):
+    """lib.rs:289-300 patch_cycle (+ the two frame-size-policy variants of lib.rs:302-313)"""
+    cases.check_patch_cycle(ctx)
+    cases.check_patch_cycle(ctx, zk.FrameSizePolicy.Uncompressed(3000))
+    cases.check_patch_cycle(ctx, zk.FrameSizePolicy.Compressed(700))
+
+
+def test_prefix_batches(ctx):
+    cases.check_prefix_batches(ctx)
+
+
 def test_cycle_tiny_buffers(ctx):
     cases.check_cycle_tiny_buffers(ctx)
     cases.check_cycle_tiny_buffers(ctx, zk.FrameSizePolicy.Uncompressed(777))

@@ -116,8 +116,8 @@ class Context:
     def last_device_ms(self) -> float: return float(self.lib.zk_ctx_last_device_ms(self._h))
 
     # ---- batch codec (the hot path) ------------------------------------------------------------
-    def compress_frames(self, data, frame_size: int = 0x200000, level: int = 0, checksum: bool = False):
-        """-> (compressed bytes (np.uint8), c_sizes, d_sizes).  Host buffers."""
+    def compress_frames(self, data, frame_size: int = 0x200000, level: int = 0, checksum: bool = False, prefix=None):
+        """-> (compressed bytes (np.uint8), c_sizes, d_sizes).  Host buffers.  prefix: raw-content prefix of every frame."""
         addr, n, keep = _buf(data)
         lib = self.lib
         cap = lib.zk_compress_bound(n, frame_size)
@@ -125,12 +125,17 @@ class Context:
         nfmax = n // max(frame_size, 1) + 2
         cs = np.zeros(nfmax, dtype=np.uint32); ds = np.zeros(nfmax, dtype=np.uint32)
         nf = c_uint32(); dl = c_size_t()
-        _check(lib.zk_compress_frames(self._h, addr, n, frame_size, level, int(checksum), dst.ctypes.data, cap,
-                                      cs.ctypes.data_as(_native.u32p), ds.ctypes.data_as(_native.u32p), nfmax, byref(nf),
-                                      byref(dl)), lib)
+        if prefix is not None:
+            paddr, pn, pkeep = _buf(prefix)
+            _check(lib.zk_compress_frames_prefix(self._h, addr, n, frame_size, level, int(checksum), paddr, pn, dst.ctypes.data, cap,
+                                                 cs.ctypes.data_as(_native.u32p), ds.ctypes.data_as(_native.u32p), nfmax, byref(nf), byref(dl)), lib)
+        else:
+            _check(lib.zk_compress_frames(self._h, addr, n, frame_size, level, int(checksum), dst.ctypes.data, cap,
+                                          cs.ctypes.data_as(_native.u32p), ds.ctypes.data_as(_native.u32p), nfmax, byref(nf),
+                                          byref(dl)), lib)
         return dst[: dl.value], cs[: nf.value].copy(), ds[: nf.value].copy()
 
-    def decompress_frames(self, comp, c_off, d_off, verify_checksum: bool = True, out: np.ndarray | None = None, need=None):
+    def decompress_frames(self, comp, c_off, d_off, verify_checksum: bool = True, out: np.ndarray | None = None, need=None, prefix=None):
         """decode frames given N+1 cumulative offsets -> (np.uint8 output, per-frame status, rc).
         need (optional, one uint32 per frame): only that many leading bytes of each frame are wanted (range reads,
         zk_decompress_frames_upto): the rest of a frame's output range is then unspecified and its checksum is not verified."""
@@ -146,9 +151,10 @@ class Context:
         nd = None if need is None else np.ascontiguousarray(need, dtype=np.uint32)
         if nd is not None and len(nd) != nf:
             raise ValueError("need: one entry per frame")
-        rc = self.lib.zk_decompress_frames_upto(self._h, addr, co.ctypes.data_as(_native.u64p), do.ctypes.data_as(_native.u64p), nf,
-                                                out.ctypes.data, None if nd is None else nd.ctypes.data_as(_native.u32p),
-                                                int(verify_checksum), st.ctypes.data_as(_native.i32p))
+        paddr, pn, pkeep = _buf(prefix) if prefix is not None else (None, 0, None)
+        rc = self.lib.zk_decompress_frames_prefix(self._h, addr, co.ctypes.data_as(_native.u64p), do.ctypes.data_as(_native.u64p), nf,
+                                                  out.ctypes.data, None if nd is None else nd.ctypes.data_as(_native.u32p),
+                                                  int(verify_checksum), st.ctypes.data_as(_native.i32p), paddr, pn)
         return out[:total], st[:nf], rc
 
 
@@ -320,6 +326,20 @@ class RawEncoder:
         _check(self.lib.zk_raw_encoder_compress(self._h, addr, n, oarr, len(mv), byref(p)), self.lib)
         return p
 
+    def compress_with_prefix(self, input, output, prefix=None) -> CompressionProgress:
+        """encode.rs:311-354: `prefix` (bytes-like, or None) becomes the raw-content prefix of a frame when passed on the
+        frame's first call; the caller keeps it alive until the frame is closed"""
+        if prefix is None:
+            return self.compress(input, output)
+        addr, n, keep = _buf(input)
+        paddr, pn, pkeep = _buf(prefix)
+        self._prefix_keep = pkeep
+        mv = memoryview(output)
+        oarr = (ctypes.c_uint8 * len(mv)).from_buffer(mv) if len(mv) else None
+        p = CompressionProgress()
+        _check(self.lib.zk_raw_encoder_compress_with_prefix(self._h, addr, n, oarr, len(mv), paddr, pn, byref(p)), self.lib)
+        return p
+
     def end_frame(self, output) -> EpilogueProgress:
         mv = memoryview(output)
         oarr = (ctypes.c_uint8 * len(mv)).from_buffer(mv) if len(mv) else None
@@ -380,6 +400,17 @@ class Encoder(io.RawIOBase):
         addr, n, keep = _buf(buf)
         c = c_size_t()
         _check(self.lib.zk_encoder_compress(self._h, addr, n, byref(c)), self.lib)
+        return int(c.value)
+
+    def compress_with_prefix(self, buf, prefix=None) -> int:
+        """encode.rs:641-665"""
+        if prefix is None:
+            return self.compress(buf)
+        addr, n, keep = _buf(buf)
+        paddr, pn, pkeep = _buf(prefix)
+        self._prefix_keep = pkeep
+        c = c_size_t()
+        _check(self.lib.zk_encoder_compress_with_prefix(self._h, addr, n, paddr, pn, byref(c)), self.lib)
         return int(c.value)
 
     def writable(self): return True
@@ -497,6 +528,20 @@ class Decoder(io.RawIOBase):
         arr = (ctypes.c_uint8 * len(mv)).from_buffer(mv)
         p = c_size_t()
         _check(self.lib.zk_decoder_decompress(self._h, arr, len(mv), byref(p)), self.lib)
+        return int(p.value)
+
+    def decompress_with_prefix(self, buf, prefix=None) -> int:
+        """decode.rs:201-270: every frame is decoded against the raw-content prefix"""
+        if prefix is None:
+            return self.decompress(buf)
+        mv = memoryview(buf)
+        if len(mv) == 0:
+            return 0
+        arr = (ctypes.c_uint8 * len(mv)).from_buffer(mv)
+        paddr, pn, pkeep = _buf(prefix)
+        self._prefix_keep = pkeep
+        p = c_size_t()
+        _check(self.lib.zk_decoder_decompress_with_prefix(self._h, arr, len(mv), paddr, pn, byref(p)), self.lib)
         return int(p.value)
 
     def readable(self): return True

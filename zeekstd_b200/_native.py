@@ -53,6 +53,9 @@ _SIGS = {
                                      u32p, u32p, c_uint32, u32p, POINTER(c_size_t)]),
     "zk_decompress_frames": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, c_int32, i32p]),
     "zk_decompress_frames_upto": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, u32p, c_int32, i32p]),
+    "zk_compress_frames_prefix": (c_int32, [c_void_p, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_size_t,
+                                            u32p, u32p, c_uint32, u32p, POINTER(c_size_t)]),
+    "zk_decompress_frames_prefix": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, u32p, c_int32, i32p, c_void_p, c_size_t]),
     "zk_compress_frames_dev": (c_int32, [c_void_p, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_void_p, c_size_t,
                                          u32p, u32p, c_uint32, u32p, POINTER(c_size_t), c_void_p]),
     "zk_decompress_frames_dev": (c_int32, [c_void_p, c_void_p, u64p, u64p, c_uint32, c_void_p, c_int32, i32p,
@@ -93,6 +96,8 @@ _SIGS = {
     "zk_raw_encoder_free": (None, [c_void_p]),
     "zk_raw_encoder_compress": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                           POINTER(CompressionProgress)]),
+    "zk_raw_encoder_compress_with_prefix": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
+                                                      POINTER(CompressionProgress)]),
     "zk_raw_encoder_end_frame": (c_int32, [c_void_p, c_void_p, c_size_t, POINTER(EpilogueProgress)]),
     "zk_raw_encoder_seek_table": (c_void_p, [c_void_p]),
     "zk_raw_encoder_into_seek_table": (c_void_p, [c_void_p]),
@@ -100,6 +105,7 @@ _SIGS = {
     "zk_raw_encoder_reset_seek_table": (None, [c_void_p]),
     "zk_encoder_free": (None, [c_void_p]),
     "zk_encoder_compress": (c_int32, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
+    "zk_encoder_compress_with_prefix": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t)]),
     "zk_encoder_end_frame": (c_int32, [c_void_p, POINTER(c_size_t)]),
     "zk_encoder_flush": (c_int32, [c_void_p]),
     "zk_encoder_finish": (c_int32, [c_void_p, u64p]),
@@ -118,6 +124,7 @@ _SIGS = {
     "zk_decode_options_into_decoder": (c_int32, [c_void_p, POINTER(c_void_p)]),
     "zk_decoder_free": (None, [c_void_p]),
     "zk_decoder_decompress": (c_int32, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
+    "zk_decoder_decompress_with_prefix": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t)]),
     "zk_decoder_reset": (None, [c_void_p]),
     "zk_decoder_set_lower_frame": (c_int32, [c_void_p, c_uint32, u64p]),
     "zk_decoder_set_upper_frame": (c_int32, [c_void_p, c_uint32, u64p]),

@@ -127,6 +127,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
         if (s.d_out) cudaFree(s.d_out);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    if (c->d_prefix) cudaFree(c->d_prefix);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -229,6 +230,7 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
     s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", 3);
     s.dws.need = need ? need + f : nullptr;
+    s.dws.prefix = c->cur_prefix_len ? c->d_prefix : nullptr; s.dws.prefix_len = c->cur_prefix_len;
     rc = zk_decode_enqueue(&s.dws, s.stream, s.d_in, sb.c_rel.data(), sb.d_rel.data(), cnt, s.d_out, verify,
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
     if (rc) return rc;
@@ -391,6 +393,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }
         tr.mark(s.stream, (int)k, 1);
         s.ews.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
+        s.ews.prefix = c->cur_prefix_len ? c->d_prefix : nullptr; s.ews.prefix_len = c->cur_prefix_len;
         rc = zk_encode_enqueue(&s.ews, s.stream, s.d_in, sb.in_len, frame_size, level, checksum, s.d_out, bound, sb.cnt);
         if (rc) { err = rc; break; }
         tr.mark(s.stream, (int)k, 2);
@@ -412,4 +415,50 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
     if (n_frames) *n_frames = nf;
     if (dst_len) *dst_len = out_pos;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prefix / patch mode: every frame is coded against the same raw-content prefix
+//   RawEncoder::compress_with_prefix   encode.rs:311-338  (cctx.ref_prefix at the start of every frame)
+//   Decoder::decompress_with_prefix    decode.rs:201-214, 246-255  (dctx.ref_prefix before the first frame and after every frame end)
+// The prefix is uploaded once per call and stays resident; K-C1 searches its tail from the first block of every frame, K-D2
+// resolves offsets that reach before a frame's first byte into it.
+// ---------------------------------------------------------------------------------------------
+static int32_t zk_ctx_set_prefix(zk_ctx* c, const uint8_t* prefix, size_t len) {
+    c->cur_prefix_len = 0;
+    if (!prefix || len == 0) return 0;
+    if (len > 0x7FFFFFFFull) return ZK_ERR_INVALID_ARG;
+    ZK_RT_OK(cudaSetDevice(c->device));
+    if (c->cap_prefix < len + 64) {
+        if (c->d_prefix) cudaFree(c->d_prefix);
+        c->d_prefix = nullptr; c->cap_prefix = 0;
+        if (cudaMalloc((void**)&c->d_prefix, len + len / 8 + 256) != cudaSuccess) return ZK_ERR_ZSTD(ZKZ_MEMORY_ALLOCATION);
+        c->cap_prefix = len + len / 8 + 256;
+    }
+    for (int i = 0; i < ZK_SLOTS; i++) if (c->slot[i].stream) cudaStreamSynchronize(c->slot[i].stream);    // nobody reads the old prefix any more
+    ZK_RT_OK(cudaMemcpy(c->d_prefix, prefix, len, cudaMemcpyHostToDevice));
+    c->cur_prefix_len = (uint32_t)len;
+    return 0;
+}
+
+extern "C" int32_t zk_compress_frames_prefix(zk_ctx* c, const uint8_t* src, size_t n, uint32_t frame_size, int32_t level, int32_t checksum,
+                                             const uint8_t* prefix, size_t prefix_len, uint8_t* dst, size_t dst_cap, uint32_t* c_sizes,
+                                             uint32_t* d_sizes, uint32_t frames_cap, uint32_t* n_frames, size_t* dst_len) {
+    if (!c) return ZK_ERR_INVALID_ARG;
+    int32_t rc = zk_ctx_set_prefix(c, prefix, prefix_len);
+    if (rc) return rc;
+    rc = zk_compress_frames(c, src, n, frame_size, level, checksum, dst, dst_cap, c_sizes, d_sizes, frames_cap, n_frames, dst_len);
+    c->cur_prefix_len = 0;
+    return rc;
+}
+
+extern "C" int32_t zk_decompress_frames_prefix(zk_ctx* c, const uint8_t* comp, const uint64_t* c_off, const uint64_t* d_off, uint32_t n,
+                                               uint8_t* dst, const uint32_t* d_need, int32_t verify, int32_t* status,
+                                               const uint8_t* prefix, size_t prefix_len) {
+    if (!c) return ZK_ERR_INVALID_ARG;
+    int32_t rc = zk_ctx_set_prefix(c, prefix, prefix_len);
+    if (rc) return rc;
+    rc = zk_decompress_frames_upto(c, comp, c_off, d_off, n, dst, d_need, verify, status);
+    c->cur_prefix_len = 0;
+    return rc;
 }

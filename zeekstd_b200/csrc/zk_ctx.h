@@ -20,6 +20,8 @@ struct zk_ctx {
     ZkSlot slot[ZK_SLOTS];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
+    uint8_t* d_prefix = nullptr; size_t cap_prefix = 0;   // device copy of the raw-content prefix of the *_prefix entry points
+    uint32_t cur_prefix_len = 0;                          // != 0 while such a call is running: every sub-batch gets the prefix
     unsigned long long launches() const {
         unsigned long long n = 0;
         for (int i = 0; i < ZK_SLOTS; i++) n += slot[i].dws.launches + slot[i].ews.launches;

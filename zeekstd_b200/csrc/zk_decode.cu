@@ -1448,8 +1448,8 @@ __device__ __forceinline__ void zk_exec2_body(ZkX2Smem& sm, const ZkDecodeArgs& 
             if (lane == 0 && s) { le_first = s_lit[s - 1]; oe_first = s_out[s - 1]; }
             uint32_t le_prev = __shfl_up_sync(0xFFFFFFFFu, le, 1), oe_prev = __shfl_up_sync(0xFFFFFFFFu, oe, 1);
             if (lane == 0) { le_prev = le_first; oe_prev = oe_first; }
-            const uint32_t ll = le - le_prev, ml = (oe - oe_prev) - ll;
-            const uint32_t o_lit = pos + oe_prev, md = o_lit + ll;          // entry-relative positions
+            const uint32_t ll = le - le_prev; uint32_t ml = (oe - oe_prev) - ll;
+            const uint32_t o_lit = pos + oe_prev; uint32_t md = o_lit + ll;  // entry-relative positions (md / ml shrink to the in-frame part of a prefix match below)
             uint32_t off = offv;
             bool bad = false;
             if (valid) {
@@ -1458,7 +1458,7 @@ __device__ __forceinline__ void zk_exec2_body(ZkX2Smem& sm, const ZkDecodeArgs& 
                     const uint32_t r = sl == 0 ? R0 : (sl == 1 ? R1 : R2);
                     bad = r <= dl; off = r - dl;
                 }
-                if (off == 0 || off > md - zstart) bad = true;
+                if (off == 0 || off > md - zstart + a.prefix_len) bad = true;
             }
             if (__any_sync(0xFFFFFFFFu, bad)) { zk_x2_abort(sm, ZKZ_CORRUPTION); break; }
             const uint32_t chunk_start = pos + __shfl_sync(0xFFFFFFFFu, oe_prev, 0);
@@ -1490,6 +1490,12 @@ __device__ __forceinline__ void zk_exec2_body(ZkX2Smem& sm, const ZkDecodeArgs& 
                             else zk_warp_copy(out + d, lit + sp, n, lane);
                         }
                     }
+                }
+                if (valid && ml > 0 && off > md - zstart) {          // the match starts in the prefix
+                    const uint32_t back = off - (md - zstart), la = ml < back ? ml : back;
+                    const uint8_t* ps = a.prefix + (a.prefix_len - back);
+                    for (uint32_t i = 0; i < la; i++) out[md + i] = ps[i];
+                    md += la; ml -= la;
                 }
                 __threadfence_block();
                 __syncwarp();
@@ -1523,6 +1529,14 @@ __device__ __forceinline__ void zk_exec2_body(ZkX2Smem& sm, const ZkDecodeArgs& 
 
             // ======== normal chunk: build the output in the ring, then flush
             zk_chunk_literals<true>(rg, lit, blk.lit_kind, blk.lit_byte, le, le_prev, o_lit, lane);      // no dependencies
+            if (a.prefix_len && valid && ml > 0 && off > md - zstart) {
+                // the match starts in the raw-content prefix that precedes every zstd frame: that part is constant data, copied now;
+                // what is left of the match (if anything) starts at the frame's first byte and is an ordinary match
+                const uint32_t back = off - (md - zstart), la = ml < back ? ml : back;
+                const uint8_t* ps = a.prefix + (a.prefix_len - back);
+                for (uint32_t i = 0; i < la; i++) rg.at(md + i) = ps[i];
+                md += la; ml -= la;
+            }
             // matches.  near: the source is still resident in the ring (distance < R/2 from the chunk start); far: it is in HBM
             // (flushed, by the start rule) and has no dependency on anything in flight.
             const uint32_t src0 = md - off;
@@ -1783,6 +1797,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     a.cap_blocks = ws->cap_blocks; a.cap_lit = ws->cap_lit - 64; a.cap_seq = ws->cap_seq;
     a.trace = nullptr;
     a.d_need = nullptr;
+    a.prefix = ws->prefix; a.prefix_len = ws->prefix ? ws->prefix_len : 0; ws->prefix = nullptr; ws->prefix_len = 0;
     if (ws->need) {
         memcpy(ws->h_need, ws->need, (size_t)n * 4);
         ZK_CUDA_OK(cudaMemcpyAsync(ws->d_need, ws->h_need, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
@@ -1841,7 +1856,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     if (per_sm < 1) per_sm = 1;
     int W = exec_warps;
     ws->prof.begin(3, stream);
-    if (!ws->exec_v1) {
+    if (!ws->exec_v1 || a.prefix_len) {          // (prefix mode exists in the second-generation kernel only)
         // second-generation kernel: <= 64 registers, so 32 warps per SM whatever the split; ring = what is left of the
         // SM's shared memory per resident entry
         if (per_sm > 8) per_sm = 8;

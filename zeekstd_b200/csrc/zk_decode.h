@@ -14,6 +14,7 @@ struct ZkDecodeArgs {                 // kernel parameter block (by value)
     uint32_t* huf_list; uint32_t* seq_list;   // compacted indices of blocks with Huffman literals / with sequences
     unsigned long long cap_blocks, cap_lit, cap_seq;
     unsigned long long* trace;        // debug: per-chunk clock64 stamps of entry 0 (env ZK_EXEC_TRACE), else nullptr
+    const uint8_t* prefix; uint32_t prefix_len;   // raw-content prefix of every zstd frame (Decoder::decompress_with_prefix, decode.rs:211-214, 246-255); device pointer or nullptr
     const uint32_t* d_need;           // per entry: only this many leading bytes are wanted (range reads); nullptr = everything
 };
 
@@ -26,6 +27,7 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     uint64_t* c_off = nullptr; uint64_t* d_off = nullptr;
     const uint32_t* need = nullptr;   // host array for the NEXT enqueue (one-shot): leading bytes wanted per entry, see ZkDecodeArgs::d_need
     uint32_t* d_need = nullptr; uint32_t* h_need = nullptr;
+    const uint8_t* prefix = nullptr; uint32_t prefix_len = 0;   // device pointer for the NEXT enqueue (one-shot, like `need`)
     uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
     bool attr_set = false; uint32_t ring_override = 0;
     bool exec_v1 = false;             // ZK_EXEC_V1=1: the first-generation (dataflow) exec kernel, kept for A/B measurements

@@ -46,7 +46,12 @@ struct ZkEncodeArgs {
     uint8_t* seqsec;                                            // ZKC_SEQSEC per block
     uint32_t* frame_csize; unsigned long long* frame_off; uint32_t* frame_hash;
     uint8_t* dst; size_t dst_cap; unsigned long long* total; uint32_t* error;
+    // raw-content prefix (RawEncoder::compress_with_prefix, encode.rs:311-338: re-applied at the start of EVERY frame): the last
+    // ptail <= ZKC_BLOCK bytes of it are staged in front of a copy of each frame's first block, so that block's match finder sees
+    // one contiguous history and needs no second pointer
+    const uint8_t* prefix; uint32_t prefix_len, ptail; uint8_t* pstage;
 };
+#define ZKC_PSLOT (2u * ZKC_BLOCK + 64u)   // per-frame staging slot: [prefix tail | first block]
 
 __device__ __forceinline__ void zkc_block_range(const ZkEncodeArgs& a, uint32_t b, size_t& lo, size_t& hi, size_t& fstart) {
     uint32_t f = b / a.blocks_per_frame, k = b % a.blocks_per_frame;
@@ -82,6 +87,19 @@ __device__ __forceinline__ uint32_t zkc_hash5(unsigned long long v) {
 // =============================================================================================
 #define ZKC_C1_WARPS 4
 
+// prefix mode: [tail of the prefix | first block of frame f] -> pstage slot f (one CTA per frame)
+__global__ void __launch_bounds__(256) zk_prefix_stage_kernel(ZkEncodeArgs a) {
+    const uint32_t f = blockIdx.x;
+    const size_t fstart = (size_t)f * a.frame_size;
+    const size_t fend = fstart + a.frame_size < a.n ? fstart + a.frame_size : a.n;
+    const uint32_t len = (uint32_t)(fend - fstart < ZKC_BLOCK ? fend - fstart : ZKC_BLOCK);
+    uint8_t* d = a.pstage + (size_t)f * ZKC_PSLOT;
+    const uint8_t* pt = a.prefix + (a.prefix_len - a.ptail);
+    for (uint32_t i = threadIdx.x; i < a.ptail; i += blockDim.x) d[i] = pt[i];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) d[a.ptail + i] = a.src[fstart + i];
+    for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) d[a.ptail + len + i] = 0;
+}
+
 template <int HLOG>
 __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArgs a) {
     __shared__ uint16_t tables[ZKC_C1_WARPS][1 << HLOG];
@@ -91,10 +109,12 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
     uint16_t* table = tables[warp];
     size_t lo, hi, fstart;
     zkc_block_range(a, b, lo, hi, fstart);
-    // history: up to one block of the same frame before `lo` is searchable (positions < 64 KiB fit the u16 table)
+    // history: up to one block of the same frame before `lo` is searchable (positions < 64 KiB fit the u16 table); the first
+    // block of a frame searches the tail of the prefix instead, through its staged copy
+    const bool pfx = a.ptail != 0 && lo == fstart;
     const size_t base = lo - fstart >= ZKC_BLOCK ? lo - ZKC_BLOCK : fstart;
-    const uint8_t* sb = a.src + base;
-    const uint32_t lo32 = (uint32_t)(lo - base), hi32 = (uint32_t)(hi - base);
+    const uint8_t* sb = pfx ? a.pstage + (size_t)(b / a.blocks_per_frame) * ZKC_PSLOT : a.src + base;
+    const uint32_t lo32 = pfx ? a.ptail : (uint32_t)(lo - base), hi32 = lo32 + (uint32_t)(hi - lo);
     for (int i = lane; i < (1 << HLOG); i += 32) table[i] = 0;
     __syncwarp();
     const uint32_t len = hi32 - lo32;
@@ -107,8 +127,8 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         const uint32_t mflimit = hi32 - 8;                  // last position where 8 bytes can be read
         const uint32_t lt_mask = (1u << lane) - 1u;
         const bool lazy = a.level >= 2;
-        // pre-insert the history so matches can reach into the previous block
-        if (a.level >= 2) {
+        // pre-insert the history so matches can reach into the previous block (or the prefix)
+        if (a.level >= 2 || pfx) {
             for (uint32_t p0 = 0; p0 < lo32; p0 += 32) {
                 const uint32_t p = p0 + lane;
                 const uint32_t hh = p < lo32 ? zkc_hash5<HLOG>(zkc_ld8(sb + p)) : (0xFFFF0000u | (uint32_t)lane);
@@ -1110,6 +1130,8 @@ static size_t zkc_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src, size_t n, uint32_t frame_size, int level,
                       int checksum, uint8_t* d_dst, size_t dst_cap, uint32_t n_frames) {
+    const uint8_t* d_prefix = ws->prefix; const uint32_t prefix_len = ws->prefix_len;     // one-shot (set by the caller for THIS batch)
+    ws->prefix = nullptr; ws->prefix_len = 0;
     ws->pending_frames = 0;
     if (n_frames == 0) return 0;
     if (frame_size == 0 || frame_size > 0x40000000u) return -(int)ZKZ_PARAM_OUT_OF_BOUND;
@@ -1130,6 +1152,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     const size_t o_foff = off; off = zkc_align(off + (size_t)n_frames * 8);
     const size_t o_fh = off; off = zkc_align(off + (size_t)n_frames * 4);
     const size_t o_tot = off; off = zkc_align(off + 16);
+    const size_t o_pst = off; if (d_prefix && prefix_len && n) off = zkc_align(off + (size_t)n_frames * ZKC_PSLOT);
     if (ws->cap < off) {
         if (ws->buf) cudaFree(ws->buf);
         ws->buf = nullptr; ws->cap = 0;
@@ -1153,6 +1176,12 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     a.lits = base + o_lits; a.stage = base + o_stage; a.seqsec = base + o_seqsec;
     a.frame_csize = (uint32_t*)(base + o_fcs); a.frame_off = (unsigned long long*)(base + o_foff); a.frame_hash = (uint32_t*)(base + o_fh);
     a.dst = d_dst; a.dst_cap = dst_cap; a.total = (unsigned long long*)(base + o_tot); a.error = (uint32_t*)(base + o_tot + 8);
+    a.prefix = d_prefix; a.prefix_len = 0; a.ptail = 0; a.pstage = base + o_pst;
+    if (d_prefix && prefix_len && n) {
+        a.prefix_len = prefix_len; a.ptail = prefix_len < ZKC_BLOCK ? prefix_len : ZKC_BLOCK;
+        ZK_LAUNCH(zk_prefix_stage_kernel, n_frames, 256, 0, stream, a);
+        ws->launches += 1;
+    }
     ZKC_CUDA_OK(cudaMemsetAsync(base + o_tot, 0, 16, stream));
     // the content checksum only needs the input: it runs beside the match finder on the side stream (one warp per frame, bound
     // by the latency of its four serial chains, so it leaves the machine to K-C1)

@@ -259,6 +259,7 @@ struct zk_raw_encoder {                    // encode.rs:266-545
     std::vector<uint8_t> out_buf;          // the frame's compressed bytes once produced
     size_t out_pos = 0; bool compressed = false;
     uint64_t next_trial = 0;               // Compressed(n) policy: input size at which the next trial compression runs
+    const uint8_t* prefix = nullptr; size_t prefix_len = 0;   // raw-content prefix of the frame being built (encode.rs:332-338: taken at the frame's first compress call)
 
     uint32_t uncompressed_limit() const { return kind == ZK_POLICY_UNCOMPRESSED ? std::min(kMaxFrameSize, size) : kMaxFrameSize; }
     size_t remaining_frame_size() const { return uncompressed_limit() - frame_d_size; }             // :528-535
@@ -276,13 +277,13 @@ struct zk_raw_encoder {                    // encode.rs:266-545
         out_buf.resize(cap);
         uint32_t cs = 0, ds = 0, nf = 0; size_t len = 0;
         static const uint8_t dummy = 0;
-        int32_t rc = zk_compress_frames(ctx, in_buf.empty() ? &dummy : in_buf.data(), in_buf.size(), (uint32_t)std::max<size_t>(in_buf.size(), 1),
-                                        level, checksum, out_buf.data(), cap, &cs, &ds, 1, &nf, &len);
+        int32_t rc = zk_compress_frames_prefix(ctx, in_buf.empty() ? &dummy : in_buf.data(), in_buf.size(), (uint32_t)std::max<size_t>(in_buf.size(), 1),
+                                               level, checksum, prefix, prefix_len, out_buf.data(), cap, &cs, &ds, 1, &nf, &len);
         if (rc) return rc;
         out_buf.resize(len);
         return 0;
     }
-    void reset_frame() { frame_c_size = 0; frame_d_size = 0; in_buf.clear(); out_buf.clear(); out_pos = 0; compressed = false; est_c = 0; next_trial = 0; }
+    void reset_frame() { frame_c_size = 0; frame_d_size = 0; in_buf.clear(); out_buf.clear(); out_pos = 0; compressed = false; est_c = 0; next_trial = 0; prefix = nullptr; prefix_len = 0; }
 };
 
 extern "C" int32_t zk_encode_options_into_raw_encoder(zk_encode_options* o, zk_raw_encoder** out) {
@@ -316,7 +317,12 @@ extern "C" int32_t zk_raw_encoder_end_frame(zk_raw_encoder* e, uint8_t* output, 
 }
 
 extern "C" int32_t zk_raw_encoder_compress(zk_raw_encoder* e, const uint8_t* input, size_t in_len, uint8_t* output, size_t out_len,
-                                           zk_compression_progress* prog) {                          // :311-354, :398
+                                           zk_compression_progress* prog) {                          // :398
+    return zk_raw_encoder_compress_with_prefix(e, input, in_len, output, out_len, nullptr, 0, prog);
+}
+
+extern "C" int32_t zk_raw_encoder_compress_with_prefix(zk_raw_encoder* e, const uint8_t* input, size_t in_len, uint8_t* output, size_t out_len,
+                                                       const uint8_t* prefix, size_t prefix_len, zk_compression_progress* prog) {   // :311-354
     if (e->is_frame_complete()) {                                                                    // :317-327
         size_t out_progress = 0;
         while (out_progress < out_len) {
@@ -330,6 +336,7 @@ extern "C" int32_t zk_raw_encoder_compress(zk_raw_encoder* e, const uint8_t* inp
         return 0;
     }
     size_t limit = std::min(in_len, e->remaining_frame_size());                                      // :329
+    if (prefix && e->frame_d_size == 0) { e->prefix = prefix; e->prefix_len = prefix_len; }         // :332-338: referenced at the beginning of a frame
     e->in_buf.insert(e->in_buf.end(), input, input + limit);
     e->frame_d_size += (uint32_t)limit;
     if (e->kind == ZK_POLICY_COMPRESSED && e->frame_d_size >= e->size && e->frame_d_size >= e->next_trial) {
@@ -367,6 +374,7 @@ struct zk_encoder {
     std::vector<uint8_t> batch;            // complete + partial frames not yet compressed (Uncompressed policy)
     std::vector<uint8_t> stage;
     size_t batch_frames = 64;
+    const uint8_t* prefix = nullptr; size_t prefix_len = 0;   // prefix of the frames in `batch` (compress_with_prefix)
 
     int32_t sink(const uint8_t* p, size_t n) {
         if (!n) return 0;
@@ -385,8 +393,8 @@ struct zk_encoder {
         std::vector<uint32_t> cs(nfmax), ds(nfmax);
         uint32_t nf = 0; size_t len = 0;
         static const uint8_t dummy = 0;
-        int32_t rc = zk_compress_frames(raw.ctx, count ? batch.data() : &dummy, count, fs, raw.level, raw.checksum, stage.data(), cap, cs.data(), ds.data(),
-                                        nfmax, &nf, &len);
+        int32_t rc = zk_compress_frames_prefix(raw.ctx, count ? batch.data() : &dummy, count, fs, raw.level, raw.checksum, prefix, prefix_len, stage.data(), cap,
+                                               cs.data(), ds.data(), nfmax, &nf, &len);
         if (rc) return rc;
         for (uint32_t i = 0; i < nf; i++) { rc = zk_seek_table_log_frame(&raw.seek_table, cs[i], ds[i]); if (rc) return rc; }
         rc = sink(stage.data(), len);
@@ -413,14 +421,29 @@ extern "C" void zk_encoder_free(zk_encoder* e) { delete e; }
 extern "C" uint64_t zk_encoder_written_compressed(const zk_encoder* e) { return e->written_compressed; }
 extern "C" const zk_seek_table* zk_encoder_seek_table(const zk_encoder* e) { return &e->raw.seek_table; }
 
-extern "C" int32_t zk_encoder_compress(zk_encoder* e, const uint8_t* buf, size_t len, size_t* consumed) {     // :641-665, :692
+extern "C" int32_t zk_encoder_compress(zk_encoder* e, const uint8_t* buf, size_t len, size_t* consumed) {     // :692
+    return zk_encoder_compress_with_prefix(e, buf, len, nullptr, 0, consumed);
+}
+
+extern "C" int32_t zk_encoder_compress_with_prefix(zk_encoder* e, const uint8_t* buf, size_t len, const uint8_t* prefix, size_t prefix_len,
+                                                   size_t* consumed) {                                         // :641-665
+    if (prefix != e->prefix || prefix_len != e->prefix_len) {
+        // the batch buffer holds frames of ONE prefix: close what was buffered under the previous one first (whole frames only;
+        // a partial frame keeps the prefix it started with, as in the reference)
+        if (e->raw.kind != ZK_POLICY_COMPRESSED && !e->batch.empty()) {
+            const uint32_t fs0 = e->frame_limit();
+            const size_t whole = fs0 ? (e->batch.size() / fs0) * fs0 : 0;
+            if (whole && whole == e->batch.size()) { int32_t rc = e->flush_batch(whole, nullptr, false); if (rc) return rc; }
+        }
+        if (e->batch.empty()) { e->prefix = prefix; e->prefix_len = prefix_len; }
+    }
     if (e->raw.kind == ZK_POLICY_COMPRESSED) {
         // frame-at-a-time through the RawEncoder state machine, 128 KiB staging like the reference (:599)
         std::vector<uint8_t>& st = e->stage; st.resize(131591);
         size_t in_pos = 0;
         while (in_pos < len) {
             zk_compression_progress p{};
-            int32_t rc = zk_raw_encoder_compress(&e->raw, buf + in_pos, len - in_pos, st.data(), st.size(), &p);
+            int32_t rc = zk_raw_encoder_compress_with_prefix(&e->raw, buf + in_pos, len - in_pos, st.data(), st.size(), prefix, prefix_len, &p);
             if (rc) return rc;
             if (p.in_progress == 0 && p.out_progress == 0) break;
             rc = e->sink(st.data(), p.out_progress);
@@ -519,6 +542,7 @@ struct zk_decoder {                        // decode.rs:121-466
     uint32_t win_lo = 0, win_hi = 0; std::vector<uint8_t> window; std::vector<uint8_t> comp;
     uint64_t win_valid_end = 0;            // the window is decoded up to this decompressed offset (< d[win_hi] after a range read)
     size_t max_window_bytes = (size_t)256 << 20;
+    const uint8_t* prefix = nullptr; size_t prefix_len = 0;   // the prefix the window was decoded with (decompress_with_prefix)
 
     void reset_dctx() { read_compressed = 0; win_lo = win_hi = 0; win_valid_end = 0; window.clear(); }                           // :352-357
     int32_t check_offset(uint64_t off) const { return off > seek_table.d.back() ? ZK_ERR_OFFSET_OUT_OF_RANGE : 0; }   // :439-445
@@ -547,7 +571,7 @@ struct zk_decoder {                        // decode.rs:121-466
             need.assign(n, 0xFFFFFFFFu);
             need[n - 1] = (uint32_t)(need_end - seek_table.d[f1 - 1]);
         } else need_end = d1;
-        rc = zk_decompress_frames_upto(ctx, comp.data(), co.data(), dof.data(), n, window.data(), need.empty() ? nullptr : need.data(), 1, nullptr);
+        rc = zk_decompress_frames_prefix(ctx, comp.data(), co.data(), dof.data(), n, window.data(), need.empty() ? nullptr : need.data(), 1, nullptr, prefix, prefix_len);
         if (rc) { win_lo = win_hi = 0; win_valid_end = 0; return rc; }
         win_lo = f0; win_hi = f1; win_valid_end = need_end;
         return 0;
@@ -583,7 +607,16 @@ extern "C" int32_t zk_decode_options_into_decoder(zk_decode_options* o, zk_decod
 }
 extern "C" void zk_decoder_free(zk_decoder* d) { delete d; }
 
-extern "C" int32_t zk_decoder_decompress(zk_decoder* d, uint8_t* buf, size_t len, size_t* produced) {           // :201-270, :314
+extern "C" int32_t zk_decoder_decompress(zk_decoder* d, uint8_t* buf, size_t len, size_t* produced) {           // :314
+    return zk_decoder_decompress_with_prefix(d, buf, len, nullptr, 0, produced);
+}
+
+extern "C" int32_t zk_decoder_decompress_with_prefix(zk_decoder* d, uint8_t* buf, size_t len, const uint8_t* prefix, size_t prefix_len,
+                                                     size_t* produced) {                                        // :201-270
+    if (prefix != d->prefix || prefix_len != d->prefix_len) {      // frames decoded under another prefix are not reusable
+        d->win_lo = d->win_hi = 0; d->win_valid_end = 0;
+        d->prefix = prefix; d->prefix_len = prefix_len;
+    }
     size_t progress = 0;
     const uint32_t nframes = d->seek_table.num_frames();
     while (d->offset < d->offset_limit && progress < len && nframes) {
