@@ -289,6 +289,32 @@ __device__ __forceinline__ bool zk_event_sleep(unsigned long long* bar, uint32_t
 #endif
 
 // -------------------------------------------------------------------------------------------
+// TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one thread arms the barrier with
+// the byte count and issues the copy; the data lands without passing through registers and whoever needs it waits on the
+// barrier's phase.  Addresses and sizes are multiples of 16 bytes.
+// -------------------------------------------------------------------------------------------
+#ifndef ZK_EMUL
+__device__ __forceinline__ void zk_mbar_init(unsigned long long* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(zk_smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void zk_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(zk_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(zk_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(zk_smem_u32(bar)) : "memory");
+}
+// returns false if the phase did not complete within ~2^22 polls (seconds): a lost copy must become an error, not a hung GPU
+__device__ __forceinline__ bool zk_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok && spin < (1u << 22); spin++)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(zk_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+#else
+// emulation: the barrier word counts completed phases; a copy completes at once
+__device__ __forceinline__ void zk_mbar_init(unsigned long long* bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void zk_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) { memcpy(dst_smem, src_gmem, bytes); *(volatile unsigned long long*)bar = *bar + 1; }
+__device__ __forceinline__ bool zk_mbar_wait(unsigned long long* bar, uint32_t parity) { while ((uint32_t)(*(volatile unsigned long long*)bar & 1) == parity) emu::yield(); return true; }
+#endif
+
+// -------------------------------------------------------------------------------------------
 // XXH64 (A.8), seed 0, of p[0..len) by one warp; the result is valid in every lane.
 //
 // The four accumulators are four serial chains (acc = rotl(acc + in * P2, 31) * P1 per 32-byte stripe), so one frame

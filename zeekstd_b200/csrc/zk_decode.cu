@@ -426,6 +426,248 @@ __global__ void __launch_bounds__(32 * ZK_SEQ_WARPS) zk_seq_kernel(ZkDecodeArgs 
 }
 
 // =============================================================================================
+// K-D1s (second generation): the same decode, cut into what MUST be serial and what need not be.
+//
+// A sequence bitstream is one serial chain: the next FSE states depend on bits whose position depends on the current
+// states' cells.  The first kernel ran the whole per-sequence work (~110 dependent instructions: extra-bit reads, value
+// arithmetic, repeat-offset history, three stores, refills from global memory) on that chain -- about 1 000 cycles per
+// sequence.  Here
+//   * the bitstream is staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, four 512-byte tiles per
+//     chain, refilled ahead of the cursor), so a bit field anywhere near the cursor is two shared-memory loads and a
+//     funnel shift -- no bit buffer, no refill branches, no global latency on the chain;
+//   * a CHAIN LANE only walks the states: three cell loads, the sum of the extra-bit counts, one 32-bit window for the
+//     three state updates, and one 16-byte record {cells, cursor} per sequence (~40 instructions);
+//   * after every 32 steps ALL lanes turn the records into values: extra bits, literal / match lengths, two warp scans for
+//     the cumulative ends, bounds checks, coalesced stores; the repeat-offset history -- a serial state machine -- is run
+//     warp-uniformly over the FEW sequences that use a repeat code (explicit offsets just shift it).
+// Four chains per warp (lanes 0, 8, 16, 24) share every issued instruction of the chain phase.
+// =============================================================================================
+#define ZK_S2_NCH 4
+#define ZK_S2_TILE 512u
+#define ZK_S2_RING_BYTES 2048u            // four tiles: the cursor's tile, the two below it, one being refilled
+struct ZkSeq2Chain {
+    ZkSeqSlot t;                           // thin cells + build scratch (zk_locate_seq_tables / zk_build_seq_table)
+    alignas(128) uint32_t ring[ZK_S2_RING_BYTES / 4];   // staged bitstream (bulk copies want 16-byte aligned shared addresses): byte at offset o from gbase lives at ring byte o & 2047
+    uint4 rec[32];                         // per step: {LL cell, OF cell, ML cell, bit cursor before the extra bits}
+    alignas(8) unsigned long long bar[4];  // one mbarrier per tile slot
+    uint32_t lit_end, out_end, r0, r1, r2; // carries of the helper phase
+    int st;
+};
+
+// the 32 bits just below bit position cur (MSB = bit cur - 1) of the staged stream
+__device__ __forceinline__ uint32_t zk_s2_window(const uint32_t* ring, uint32_t cur) {
+    const uint32_t t = cur - 1u, wi = t >> 5, sh = 31u - (t & 31u);
+    return __funnelshift_l(ring[(wi - 1u) & (ZK_S2_RING_BYTES / 4 - 1)], ring[wi & (ZK_S2_RING_BYTES / 4 - 1)], sh);
+}
+__device__ __forceinline__ uint32_t zk_s2_bits(const uint32_t* ring, uint32_t cur, uint32_t n) {       // n in [0, 31]
+    return __funnelshift_l(zk_s2_window(ring, cur), 0u, n);
+}
+
+__global__ void __launch_bounds__(32) zk_seq2_kernel(ZkDecodeArgs a) {
+    ZK_DYN_SMEM(smem);
+    ZkSeqTabs* tb = (ZkSeqTabs*)smem;
+    ZkSeq2Chain* chains = (ZkSeq2Chain*)(smem + ((sizeof(ZkSeqTabs) + 127) & ~(size_t)127));
+    const int lane = threadIdx.x & 31;
+    const int myc = lane >> 3;                                     // the chain this lane belongs to ...
+    const bool chain_lane = (lane & 7) == 0;                       // ... and whether it walks it
+    for (int i = lane; i < 36; i += 32) tb->ll_base[i] = ZK_LL_BASE[i];
+    for (int i = lane; i < 53; i += 32) tb->ml_base[i] = ZK_ML_BASE[i];
+    if (chain_lane) for (int k = 0; k < 4; k++) zk_mbar_init(&chains[myc].bar[k], 1);
+#ifndef ZK_EMUL
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    __syncwarp();
+    if (a.counters->overflow) return;
+    const uint32_t n = a.counters->n_seq_blocks;
+    uint32_t tile_uses = 0;                                        // tiles this chain lane has issued so far (slot = use & 3, parity = (use >> 2) & 1)
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&a.work_counter[0], 1u);
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        const uint32_t first = g * ZK_S2_NCH;
+        if (first >= n) break;
+        ZkSeq2Chain& ch = chains[myc];
+        // ---------------- per chain: tables, stream geometry, first tiles, initial states (chain lanes, side by side)
+        uint32_t bidx = 0, remaining = 0, done = 0, cur = 0, sb_bit = 0, s_l = 0, s_o = 0, s_m = 0, seq_base = 0, lit_size = 0;
+        const uint8_t* gbase = nullptr;
+        int next_issue = -1, next_wait = -1, top_tile = 0; uint32_t stream_end_off = 0, use0 = 0;
+        bool live = false;
+        if (chain_lane) {
+            ch.st = 0; ch.lit_end = 0; ch.out_end = 0; ch.r0 = ZK_SYM_MAKE(0, 0); ch.r1 = ZK_SYM_MAKE(1, 0); ch.r2 = ZK_SYM_MAKE(2, 0);
+            const uint32_t my = first + (uint32_t)myc;
+            if (my < n) {
+                bidx = a.seq_list[my];
+                ZkBlock blk; blk.entry = 0xFFFFFFFFu;
+                if (bidx < a.cap_blocks) blk = a.blocks[bidx];
+                if (blk.entry < a.n_entries && a.entries[blk.entry].status == 0) {
+                    live = true;
+                    const uint8_t* ebase = a.comp + a.c_off[blk.entry];
+                    const uint8_t* b = ebase + blk.src;
+                    uint32_t bits_off = 0;
+                    int st = zk_locate_seq_tables(ch.t, b, blk.size, blk.ll_ref < 0, blk.of_ref < 0, blk.ml_ref < 0, &bits_off);
+                    if (!st && blk.ll_ref >= 0) { const ZkBlock& rb = a.blocks[blk.ll_ref]; uint32_t d; st = zk_locate_seq_tables(ch.t, ebase + rb.src, rb.size, true, false, false, &d); }
+                    if (!st && blk.of_ref >= 0) { const ZkBlock& rb = a.blocks[blk.of_ref]; uint32_t d; st = zk_locate_seq_tables(ch.t, ebase + rb.src, rb.size, false, true, false, &d); }
+                    if (!st && blk.ml_ref >= 0) { const ZkBlock& rb = a.blocks[blk.ml_ref]; uint32_t d; st = zk_locate_seq_tables(ch.t, ebase + rb.src, rb.size, false, false, true, &d); }
+                    for (int t = 0; t < 3 && !st; t++) st = zk_build_seq_table(ch.t, t);
+                    const uint8_t* sp = b + bits_off; const uint32_t sn = blk.size - bits_off;
+                    if (!st && (sn == 0 || sp[sn - 1] == 0)) st = ZKZ_CORRUPTION;
+                    if (!st) {
+                        gbase = (const uint8_t*)((uintptr_t)sp & ~(uintptr_t)15);
+                        sb_bit = (uint32_t)(sp - gbase) * 8u;
+                        stream_end_off = (uint32_t)(sp - gbase) + sn;                       // byte offset of the end of the stream from gbase
+                        cur = sb_bit + (sn - 1) * 8u + (uint32_t)zk_highbit(sp[sn - 1]);     // the end mark itself is not data
+                        top_tile = (int)((stream_end_off - 1) / ZK_S2_TILE);
+                        next_issue = top_tile; next_wait = top_tile; use0 = tile_uses;
+                        remaining = blk.nseq; seq_base = blk.seq_base; lit_size = blk.lit_size;
+                    }
+                    ch.st = st;
+                }
+            }
+        }
+        // ---------------- tiles of 32 steps
+        for (;;) {
+            uint32_t cnt = 0;
+            if (chain_lane && remaining && ch.st == 0) {
+                // tiles: the cursor's tile jc and the two below it must have landed; everything above jc is dead (the records of
+                // the previous steps were consumed), so the copies may run down to jc - 3
+                const int jc = (int)(((cur ? cur - 1u : 0u) >> 3) / ZK_S2_TILE);
+                while (next_issue >= 0 && next_issue >= jc - 3) {
+                    const uint32_t off = (uint32_t)next_issue * ZK_S2_TILE;
+                    uint32_t bytes = stream_end_off - off; bytes = bytes > ZK_S2_TILE ? ZK_S2_TILE : ((bytes + 15u) & ~15u);   // (16 readable bytes follow every buffer)
+                    zk_bulk_g2s((uint8_t*)ch.ring + (off & (ZK_S2_RING_BYTES - 1)), gbase + off, bytes, &ch.bar[tile_uses & 3u]);
+                    tile_uses++; next_issue--;
+                }
+                while (next_wait >= 0 && next_wait >= jc - 2) {
+                    const uint32_t u = use0 + (uint32_t)(top_tile - next_wait);
+                    if (!zk_mbar_wait(&ch.bar[u & 3u], (u >> 2) & 1u)) {
+                        printf("zk_seq2: tile wait timed out: block %u tile %d top %d use %u use0 %u jc %d cur %u\n", bidx, next_wait, top_tile, u, use0, jc, cur);
+                        ch.st = ZKZ_GENERIC;
+                    }
+                    next_wait--;
+                }
+                if (done == 0) {                                                          // initial states (A.5: LL, OF, ML)
+                    const int ll_log = ch.t.tbl_log[0], of_log = ch.t.tbl_log[1], ml_log = ch.t.tbl_log[2];
+                    if (cur < sb_bit + (uint32_t)(ll_log + of_log + ml_log)) ch.st = ZKZ_CORRUPTION;
+                    else {
+                        s_l = zk_s2_bits(ch.ring, cur, (uint32_t)ll_log); cur -= (uint32_t)ll_log;
+                        s_o = zk_s2_bits(ch.ring, cur, (uint32_t)of_log); cur -= (uint32_t)of_log;
+                        s_m = zk_s2_bits(ch.ring, cur, (uint32_t)ml_log); cur -= (uint32_t)ml_log;
+                    }
+                }
+                if (ch.st == 0) {
+                    cnt = remaining < 32u ? remaining : 32u;
+                    const bool last_tile = cnt == remaining;
+                    bool over = false;
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        const uint32_t cl = ch.t.ll[s_l], co = ch.t.of[s_o], cm = ch.t.ml[s_m];
+                        ch.rec[k] = make_uint4(cl, co, cm, cur);
+                        const uint32_t eb = ZK_CELL_CODE(co) + ZK_CELL_ADD(cm) + ZK_CELL_ADD(cl);
+                        const uint32_t nl = ZK_CELL_NB(cl), nm = ZK_CELL_NB(cm), no = ZK_CELL_NB(co);
+                        const bool upd = !(last_tile && k + 1 == cnt);                   // no state update after the block's last sequence
+                        const uint32_t need_bits = eb + (upd ? nl + nm + no : 0u);
+                        if (cur - sb_bit < need_bits) { over = true; cnt = k; break; }    // the stream is shorter than its sequences need
+                        cur -= eb;
+                        if (upd) {
+                            const uint32_t w = zk_s2_window(ch.ring, cur);
+                            s_l = ZK_CELL_BASE(cl) + __funnelshift_l(w, 0u, nl);
+                            s_m = ZK_CELL_BASE(cm) + __funnelshift_l(w << nl, 0u, nm);
+                            s_o = ZK_CELL_BASE(co) + __funnelshift_l(w << (nl + nm), 0u, no);
+                            cur -= nl + nm + no;
+                        }
+                    }
+                    if (over) ch.st = ZKZ_CORRUPTION;
+                    remaining -= cnt; 
+                    if (over) remaining = 0;
+                }
+            }
+            __syncwarp();
+            // ---------------- helper phase: every lane, one chain after the other
+            uint32_t any = 0;
+#pragma unroll 1
+            for (int cc = 0; cc < ZK_S2_NCH; cc++) {
+                const uint32_t ncc = __shfl_sync(0xFFFFFFFFu, cnt, cc * 8);
+                if (ncc == 0) continue;
+                any = 1;
+                ZkSeq2Chain& hc = chains[cc];
+                const uint32_t sbase = __shfl_sync(0xFFFFFFFFu, seq_base, cc * 8), sdone = __shfl_sync(0xFFFFFFFFu, done, cc * 8);
+                const uint32_t lsz = __shfl_sync(0xFFFFFFFFu, lit_size, cc * 8);
+                const bool act = (uint32_t)lane < ncc;
+                uint32_t llv = 0, mlv = 0, ofv = 4;                                       // inactive lanes: explicit offsets that push nothing (masked below)
+                if (act) {
+                    const uint4 r = hc.rec[lane];
+                    const uint32_t ofc = ZK_CELL_CODE(r.y), mlb = ZK_CELL_ADD(r.z), llb = ZK_CELL_ADD(r.x);
+                    uint32_t c = r.w;
+                    ofv = (1u << ofc) + zk_s2_bits(hc.ring, c, ofc); c -= ofc;
+                    mlv = tb->ml_base[ZK_CELL_CODE(r.z)] + zk_s2_bits(hc.ring, c, mlb); c -= mlb;
+                    llv = tb->ll_base[ZK_CELL_CODE(r.x)] + zk_s2_bits(hc.ring, c, llb);
+                }
+                // cumulative ends: two inclusive warp scans on top of the chain's carries
+                uint32_t le = llv, oe = llv + mlv;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, le, d), y = __shfl_up_sync(0xFFFFFFFFu, oe, d);
+                    if (lane >= d) { le += x; oe += y; }
+                }
+                le += hc.lit_end; oe += hc.out_end;
+                // bounded after EVERY sequence (a tile adds < 2^23, the carries are <= 2^17: no wrap can hide an overflow)
+                const bool badv = act && (le > lsz || oe > ZK_BLOCK_MAX);
+                // repeat-offset history (A.5), symbolic with respect to the state entering the block: explicit offsets only shift it,
+                // so the serial part runs over the sequences that USE a repeat code
+                uint32_t r0 = hc.r0, r1 = hc.r1, r2 = hc.r2, off = ofv - 3u;
+                const uint32_t repm = __ballot_sync(0xFFFFFFFFu, act && ofv <= 3u);
+                const uint32_t idxv = ofv - 1u + (llv == 0u ? 1u : 0u);                 // meaningful on repeat lanes only
+                uint32_t m = repm; int lastpos = 0; bool badr = false;
+                for (;;) {
+                    const int j = m ? __ffs((int)m) - 1 : (int)ncc;                      // next repeat lane, or the end of the tile
+                    const int cnte = j - lastpos;                                        // explicit offsets since the last repeat lane
+                    if (cnte > 0) {
+                        const uint32_t e1 = __shfl_sync(0xFFFFFFFFu, off, j - 1);
+                        const uint32_t e2 = __shfl_sync(0xFFFFFFFFu, off, cnte > 1 ? j - 2 : 0), e3 = __shfl_sync(0xFFFFFFFFu, off, cnte > 2 ? j - 3 : 0);
+                        const uint32_t o0 = r0, o1 = r1;
+                        r0 = e1; r1 = cnte > 1 ? e2 : o0; r2 = cnte > 2 ? e3 : (cnte == 2 ? o0 : o1);
+                    }
+                    if (!m) break;
+                    const uint32_t idx = __shfl_sync(0xFFFFFFFFu, idxv, j);
+                    uint32_t o;
+                    if (idx == 0) o = r0;
+                    else {
+                        if (idx == 3) { if (r0 & ZK_SYM) o = r0 + 1u; else { o = r0 - 1u; if (o == 0) badr = true; } }
+                        else o = idx == 1 ? r1 : r2;
+                        if (idx != 1) r2 = r1;
+                        r1 = r0; r0 = o;
+                    }
+                    if (lane == j) off = o;
+                    lastpos = j + 1; m &= m - 1;
+                }
+                if (act) {
+                    const uint32_t at = sbase + sdone + (uint32_t)lane;
+                    a.seq_lit_end[at] = le; a.seq_out_end[at] = oe; a.seq_off[at] = off;
+                }
+                const bool anybad = __any_sync(0xFFFFFFFFu, badv) || badr;
+                if (lane == (int)ncc - 1) { hc.lit_end = le; hc.out_end = oe; }
+                if (lane == 0) { hc.r0 = r0; hc.r1 = r1; hc.r2 = r2; if (anybad && hc.st == 0) hc.st = ZKZ_CORRUPTION; }
+            }
+            __syncwarp();
+            if (chain_lane) { done += cnt; if (ch.st != 0) remaining = 0; }
+            if (!any) break;
+        }
+        // ---------------- results of the block
+        if (chain_lane) {     // copies issued ahead but never needed must have landed before the next block reuses the ring
+            while (next_wait > next_issue) { const uint32_t u = use0 + (uint32_t)(top_tile - next_wait); zk_mbar_wait(&ch.bar[u & 3u], (u >> 2) & 1u); next_wait--; }
+        }
+        if (chain_lane && live) {
+            int st = ch.st;
+            if (!st && cur != sb_bit) st = ZKZ_CORRUPTION;                                // every bit of the stream is consumed, no more
+            if (!st && ch.out_end + (lit_size - ch.lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
+            a.blocks[bidx].rep_out[0] = ch.r0; a.blocks[bidx].rep_out[1] = ch.r1; a.blocks[bidx].rep_out[2] = ch.r2;
+            a.blocks[bidx].regen = ch.out_end + (lit_size - ch.lit_end);
+            a.blocks[bidx].status = st ? -st : 0;
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
 // K-D1h: Huffman literal decode -- one LANE per Huffman stream (4 lanes per 4-stream block).
 // =============================================================================================
 #define ZK_HUF_SLOTS 8            // blocks per warp-CTA; 8 x 3.1 KiB -> 9 CTAs / SM
@@ -1845,7 +2087,15 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     ws->prof.end(2, hs);
     if (hs != stream) ZK_CUDA_OK(cudaEventRecord(ws->ev_huf, hs));
     ws->prof.begin(1, stream);
-    ZK_LAUNCH(zk_seq_kernel, gs, 32 * ZK_SEQ_WARPS, seq_smem, stream, a);
+    if (ws->seq_v1) ZK_LAUNCH(zk_seq_kernel, gs, 32 * ZK_SEQ_WARPS, seq_smem, stream, a);
+    else {
+        const size_t seq2_smem = ((sizeof(ZkSeqTabs) + 127) & ~(size_t)127) + sizeof(ZkSeq2Chain) * ZK_S2_NCH;
+        if (!ws->attr_set2) { ZK_CUDA_OK(cudaFuncSetAttribute(zk_seq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq2_smem)); ws->attr_set2 = true; }
+        uint32_t g2 = (uint32_t)sms * ws->seq2_ctas;
+        const size_t need2 = est_blocks / ZK_S2_NCH + 1;
+        if (need2 < g2) g2 = (uint32_t)need2;
+        ZK_LAUNCH(zk_seq2_kernel, g2, 32, seq2_smem, stream, a);
+    }
     ws->prof.end(1, stream);
     if (hs != stream) ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_huf, 0));
     // exec stage: ring size / warps per entry chosen from how many entries share the machine
@@ -1856,7 +2106,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     if (per_sm < 1) per_sm = 1;
     int W = exec_warps;
     ws->prof.begin(3, stream);
-    if (!ws->exec_v1 || a.prefix_len) {          // (prefix mode exists in the second-generation kernel only)
+    if (ws->exec_v2 || a.prefix_len) {           // (prefix mode exists in the in-order kernel only)
         // second-generation kernel: <= 64 registers, so 32 warps per SM whatever the split; ring = what is left of the
         // SM's shared memory per resident entry
         if (per_sm > 8) per_sm = 8;

@@ -30,7 +30,8 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     const uint8_t* prefix = nullptr; uint32_t prefix_len = 0;   // device pointer for the NEXT enqueue (one-shot, like `need`)
     uint32_t* huf_list = nullptr; uint32_t* seq_list = nullptr;
     bool attr_set = false; uint32_t ring_override = 0;
-    bool exec_v1 = false;             // ZK_EXEC_V1=1: the first-generation (dataflow) exec kernel, kept for A/B measurements
+    bool seq_v1 = false, attr_set2 = false; uint32_t seq2_ctas = 6;   // ZK_SEQ_V1=1: the first-generation FSE kernel; persistent CTAs per SM of the second
+    bool exec_v2 = false;             // ZK_EXEC_V2=1: the in-order exec kernel (zk_exec2_kernel) for every batch, not only in prefix mode
     uint32_t huf_pad = 0;             // extra dynamic smem per Huffman CTA: fewer resident CTAs -> more L1 for the streams (tuning)
     unsigned long long* trace = nullptr;
     int share = 1;                    // how many batches share the GPU concurrently (host pipeline depth)
