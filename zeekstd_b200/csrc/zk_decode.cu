@@ -516,7 +516,9 @@ __global__ void __launch_bounds__(32) zk_seq2_kernel(ZkDecodeArgs a) {
                         sb_bit = (uint32_t)(sp - gbase) * 8u;
                         stream_end_off = (uint32_t)(sp - gbase) + sn;                       // byte offset of the end of the stream from gbase
                         cur = sb_bit + (sn - 1) * 8u + (uint32_t)zk_highbit(sp[sn - 1]);     // the end mark itself is not data
-                        top_tile = (int)((stream_end_off - 1) / ZK_S2_TILE);
+                        // tiles are staged from the CURSOR's tile downwards: when the end mark is the first byte of a tile, that tile holds
+                        // no data (the mark was read above), and counting it would put five tiles in flight on four slots
+                        top_tile = (int)(((cur ? cur - 1u : 0u) >> 3) / ZK_S2_TILE);
                         next_issue = top_tile; next_wait = top_tile; use0 = tile_uses;
                         remaining = blk.nseq; seq_base = blk.seq_base; lit_size = blk.lit_size;
                     }
@@ -1538,9 +1540,12 @@ struct ZkX2Smem {
 #define ZK_X2_HINT_NS 20000u               // upper bound of one sleep (a missed wake-up costs at most this)
 
 __device__ __forceinline__ void zk_x2_abort(ZkX2Smem& sm, int code) {
-    atomicCAS(&sm.abort_code, 0, code);
-    __threadfence_block();
-    zk_event_signal(&sm.ev_done); zk_event_signal(&sm.ev_flush);
+    // exactly ONE thread of the CTA ever signals the abort: an event has an arrival count of one, and a warp-wide arrive
+    // (32 arrivals in one instruction) would underflow it
+    if (atomicCAS(&sm.abort_code, 0, code) == 0) {
+        __threadfence_block();
+        zk_event_signal(&sm.ev_done); zk_event_signal(&sm.ev_flush);
+    }
 }
 __device__ __forceinline__ bool zk_x2_aborted(ZkX2Smem& sm) { return __any_sync(0xFFFFFFFFu, *(volatile int*)&sm.abort_code != 0); }
 
@@ -1946,7 +1951,8 @@ static int zk_grow(void** p, size_t* cap, size_t need, size_t elem) {
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
     size_t want = need + need / 8 + 64;
-    if (cudaMalloc(p, want * elem) != cudaSuccess) { *p = nullptr; return -(int)ZKZ_MEMORY_ALLOCATION; }
+    cudaError_t ce = cudaMalloc(p, want * elem);
+    if (ce != cudaSuccess) { fprintf(stderr, "zeekstd_b200: cudaMalloc(%zu bytes) failed in the decode workspace: %s\n", want * elem, cudaGetErrorString(ce)); (void)cudaGetLastError(); *p = nullptr; return -(int)ZKZ_MEMORY_ALLOCATION; }
     *cap = want;
     return 0;
 }
@@ -2016,7 +2022,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     if (n == 0) return 0;
     unsigned long long total_d = d_off[n] - d_off[0];
     // optimistic scratch sizing; the scan kernel reports exact needs and zk_decode_collect retries if exceeded
-    size_t need_blocks = (size_t)(total_d / ZK_BLOCK_MAX) * 2 + 4 * (size_t)n + 64;
+    size_t need_blocks = (size_t)(total_d / 32768u) + 4 * (size_t)n + 64;      // this codec's own encoder cuts 32 KiB blocks (libzstd: 128 KiB)
     size_t need_lit = (size_t)total_d + 16 * need_blocks;
     size_t need_seq = (size_t)(total_d / 4) + 1024;
     if (need_blocks < ws->want_blocks) need_blocks = ws->want_blocks;
@@ -2181,5 +2187,7 @@ int zk_decode_batch(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp, 
         rc = zk_decode_collect(ws, stream, status_out);
         if (rc != ZK_ST_RETRY) return rc;
     }
+    fprintf(stderr, "zeekstd_b200: decode scratch still too small after growing to the exact needs (blocks %zu lit %zu seq %zu; caps %zu %zu %zu)\n",
+            ws->want_blocks, ws->want_lit, ws->want_seq, ws->cap_blocks, ws->cap_lit, ws->cap_seq);
     return -(int)ZKZ_MEMORY_ALLOCATION;
 }
