@@ -112,6 +112,9 @@ extern "C" int32_t zk_ctx_create(int32_t device_ordinal, uint32_t flags, zk_ctx*
         c->slot[i].ews.sm_count = c->sm_count;
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    if (zk_env_size("ZK_HOST_COPY_STREAMS", 1) != 0) {
+        cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&c->down, cudaStreamNonBlocking);
+    }
     *out = c;
     return 0;
 }
@@ -128,6 +131,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
         if (s.d_out) cudaFree(s.d_out);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    if (c->up) cudaStreamDestroy(c->up);
+    if (c->down) cudaStreamDestroy(c->down);
     if (c->d_prefix) cudaFree(c->d_prefix);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -173,6 +178,7 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
     const size_t sub_bytes = zk_env_size("ZK_DEV_SUB_BYTES", (size_t)1 << 30);
     ZkDecodeWs* ws = &c->slot[0].dws;
     ws->share = 1; ws->no_side = zk_env_size("ZK_DEV_SIDE", 1) == 0;
+    ws->up = ws->down = nullptr;                           // device-resident data: nothing to copy but offsets and statuses
     cudaEventRecord(c->ev0, st);
     int32_t worst = 0;
     for (uint32_t first = 0; first < n;) {
@@ -225,9 +231,11 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
     if (rc) return rc;
     sb.c_rel.resize(cnt + 1); sb.d_rel.resize(cnt + 1);
     for (uint32_t j = 0; j <= cnt; j++) { sb.c_rel[j] = c_off[f + j] - c_off[f]; sb.d_rel[j] = d_off[f + j] - d_off[f]; }
-    if (tr) tr->mark(s.stream, k, 0);
-    ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, s.stream));
-    if (tr) tr->mark(s.stream, k, 1);
+    cudaStream_t us = c->up ? c->up : s.stream, ds = c->down ? c->down : s.stream;
+    s.dws.up = c->up; s.dws.down = c->down;
+    if (tr) tr->mark(us, k, 0);
+    ZK_RT_OK(cudaMemcpyAsync(s.d_in, comp + c_off[f], cbytes, cudaMemcpyHostToDevice, us));
+    if (tr) tr->mark(us, k, 1);
     s.dws.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
     s.dws.share = (int)zk_env_size("ZK_HOST_SHARE", 3);
     s.dws.need = need ? need + f : nullptr;
@@ -236,8 +244,9 @@ static int zk_dec_sub_enqueue(zk_ctx* c, int si, ZkSubDec& sb, const uint8_t* co
                            (int)zk_env_size("ZK_EXEC_WARPS", 0));
     if (rc) return rc;
     if (tr) tr->mark(s.stream, k, 2);
-    if (obytes) ZK_RT_OK(cudaMemcpyAsync(dst + d_off[f], s.d_out, obytes, cudaMemcpyDeviceToHost, s.stream));
-    if (tr) tr->mark(s.stream, k, 4);
+    if (obytes) ZK_RT_OK(cudaMemcpyAsync(dst + d_off[f], s.d_out, obytes, cudaMemcpyDeviceToHost, ds));
+    if (ds != s.stream) ZK_RT_OK(cudaEventRecord(s.dws.ev_down, ds));        // what zk_decode_collect waits for
+    if (tr) tr->mark(ds, k, 4);
     sb.busy = true;
     return 0;
 }
@@ -270,7 +279,7 @@ extern "C" int32_t zk_decompress_frames_upto(zk_ctx* c, const uint8_t* comp, con
     const size_t sub_bytes = zk_env_size("ZK_HOST_SUB_BYTES", (size_t)128 << 20);     // measured best on B200 (tools/e2e_sweep2.sh)
     ZkSubDec sub[ZK_SLOTS];
     const int NS = zk_host_slots(false);
-    const bool ramp = zk_env_size("ZK_HOST_RAMP", 0) != 0;
+    const uint32_t ramp = (uint32_t)zk_env_size("ZK_HOST_RAMP", 0);            // the first `ramp` sub-batches are 1/2^ramp ... 1/2 of the full size
     int32_t worst = 0;
     uint32_t k = 0;
     ZkTrace tr; tr.begin(c->slot[0].stream);
@@ -278,8 +287,10 @@ extern "C" int32_t zk_decompress_frames_upto(zk_ctx* c, const uint8_t* comp, con
         int si = (int)(k % NS);
         int rc = zk_dec_sub_finish(c, si, sub[si], comp, c_off, d_off, dst, verify, status, d_need);
         if (rc && !worst) worst = rc;
-        // ZK_HOST_RAMP=1 (experimental, off): quarter- and half-size first sub-batches, so that the first D2H starts earlier
-        const size_t this_sub = ramp && k < 2 ? sub_bytes >> (2 - k) : sub_bytes;
+        // ZK_HOST_RAMP=r (default 0): the first r sub-batches are 1/2^r ... 1/2 of the full size, so that the output copy could start
+        // earlier.  Measured on B200 (profiles/README.md): no gain -- a sub-batch of any size spends about one frame latency in
+        // K-D2, so a small first sub-batch is not done much sooner than a full one
+        const size_t this_sub = k < ramp ? sub_bytes >> (ramp - k) : sub_bytes;
         uint32_t end = zk_next_sub(d_off, first, n, this_sub, 1u << 20);
         sub[si].first = first; sub[si].count = end - first;
         rc = zk_dec_sub_enqueue(c, si, sub[si], comp, c_off, d_off, dst, verify, &tr, (int)k, d_need);

@@ -19,6 +19,7 @@ struct zk_ctx {
     int sm_count = 148;
     ZkSlot slot[ZK_SLOTS];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t up = nullptr, down = nullptr;            // dedicated copy streams of the host-pointer decompress pipeline
     float last_ms = 0.f;
     uint8_t* d_prefix = nullptr; size_t cap_prefix = 0;   // device copy of the raw-content prefix of the *_prefix entry points
     uint32_t cur_prefix_len = 0;                          // != 0 while such a call is running: every sub-batch gets the prefix

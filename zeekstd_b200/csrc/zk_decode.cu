@@ -1968,6 +1968,9 @@ void zk_decode_ws_free(ZkDecodeWs* ws) {
     if (ws->side) cudaStreamDestroy(ws->side);
     if (ws->ev_scan) cudaEventDestroy(ws->ev_scan);
     if (ws->ev_huf) cudaEventDestroy(ws->ev_huf);
+    if (ws->ev_up) cudaEventDestroy(ws->ev_up);
+    if (ws->ev_done) cudaEventDestroy(ws->ev_done);
+    if (ws->ev_down) cudaEventDestroy(ws->ev_down);
     ws->prof.destroy();
     *ws = ZkDecodeWs();
 }
@@ -2033,8 +2036,16 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     if (rc) return rc;
     memcpy(ws->h_off, c_off, (size_t)(n + 1) * 8);
     memcpy(ws->h_off + (n + 1), d_off, (size_t)(n + 1) * 8);
-    ZK_CUDA_OK(cudaMemcpyAsync(ws->c_off, ws->h_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
-    ZK_CUDA_OK(cudaMemcpyAsync(ws->d_off, ws->h_off + (n + 1), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
+    // Host pipelines hand in dedicated copy streams (ws->up / ws->down): copies of different compute streams otherwise share
+    // copy-engine channels, where the upload of one sub-batch queues behind the status read-back of another that is still
+    // waiting for its kernels (measured: sub-batch k + 4 started its upload when sub-batch k had finished its download).
+    cudaStream_t us = ws->up ? ws->up : stream, ds = ws->down ? ws->down : stream;
+    if (us != stream && !ws->ev_up) {
+        ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_up, cudaEventDisableTiming)); ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_done, cudaEventDisableTiming));
+        ZK_CUDA_OK(cudaEventCreateWithFlags(&ws->ev_down, cudaEventDisableTiming));
+    }
+    ZK_CUDA_OK(cudaMemcpyAsync(ws->c_off, ws->h_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, us));
+    ZK_CUDA_OK(cudaMemcpyAsync(ws->d_off, ws->h_off + (n + 1), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, us));
     ZK_CUDA_OK(cudaMemsetAsync(ws->counters, 0, sizeof(ZkCounters) + 16, stream));
     ZkDecodeArgs a;
     a.comp = d_comp; a.c_off = (const unsigned long long*)ws->c_off; a.d_off = (const unsigned long long*)ws->d_off; a.dst = d_dst; a.n_entries = n;
@@ -2048,7 +2059,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     a.prefix = ws->prefix; a.prefix_len = ws->prefix ? ws->prefix_len : 0; ws->prefix = nullptr; ws->prefix_len = 0;
     if (ws->need) {
         memcpy(ws->h_need, ws->need, (size_t)n * 4);
-        ZK_CUDA_OK(cudaMemcpyAsync(ws->d_need, ws->h_need, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+        ZK_CUDA_OK(cudaMemcpyAsync(ws->d_need, ws->h_need, (size_t)n * 4, cudaMemcpyHostToDevice, us));
         a.d_need = ws->d_need; ws->need = nullptr;
     }
 #ifndef ZK_EMUL
@@ -2058,6 +2069,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
         a.trace = ws->trace;
     }
 #endif
+    if (us != stream) { ZK_CUDA_OK(cudaEventRecord(ws->ev_up, us)); ZK_CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_up, 0)); }   // also orders the caller's upload of the compressed bytes
     ws->prof.begin(0, stream);
     ZK_LAUNCH(zk_scan_kernel, (n + 127) / 128, 128, 0, stream, a);
     ws->prof.end(0, stream);
@@ -2140,8 +2152,9 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
     }
     ws->prof.end(3, stream);
     if (verify_checksum) { ws->prof.begin(4, stream); ZK_LAUNCH(zk_xxh64_kernel, (n + 3) / 4, 128, 0, stream, a); ws->prof.end(4, stream); }
-    ZK_CUDA_OK(cudaMemcpyAsync(ws->h_entries, ws->entries, (size_t)n * sizeof(ZkEntry), cudaMemcpyDeviceToHost, stream));
-    ZK_CUDA_OK(cudaMemcpyAsync(ws->h_counters, ws->counters, sizeof(ZkCounters), cudaMemcpyDeviceToHost, stream));
+    if (ds != stream) { ZK_CUDA_OK(cudaEventRecord(ws->ev_done, stream)); ZK_CUDA_OK(cudaStreamWaitEvent(ds, ws->ev_done, 0)); }
+    ZK_CUDA_OK(cudaMemcpyAsync(ws->h_entries, ws->entries, (size_t)n * sizeof(ZkEntry), cudaMemcpyDeviceToHost, ds));
+    ZK_CUDA_OK(cudaMemcpyAsync(ws->h_counters, ws->counters, sizeof(ZkCounters), cudaMemcpyDeviceToHost, ds));
     ws->launches += 4 + (verify_checksum ? 1 : 0);
     ws->pending_n = n;
     return 0;
@@ -2152,7 +2165,8 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
 int zk_decode_collect(ZkDecodeWs* ws, cudaStream_t stream, int32_t* status_out) {
     uint32_t n = ws->pending_n;
     if (n == 0) return 0;
-    ZK_CUDA_OK(cudaStreamSynchronize(stream));
+    if (ws->down && ws->ev_down) ZK_CUDA_OK(cudaEventSynchronize(ws->ev_down));     // recorded by the caller after the output copy on the download stream
+    else ZK_CUDA_OK(cudaStreamSynchronize(stream));
 #ifndef ZK_EMUL
     if (cudaGetLastError() != cudaSuccess) return -(int)ZKZ_GENERIC;
 #endif

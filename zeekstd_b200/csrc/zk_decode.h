@@ -38,6 +38,8 @@ struct ZkDecodeWs {                   // HBM scratch owned by a zk_ctx, grown on
     int prio = 0;                     // CUDA stream priority of the side stream (matches the slot's stream)
     uint32_t seq_ctas = 4, huf_ctas = 8;   // persistent CTAs per SM of the two entropy kernels (tuning: ZK_SEQ_CTAS / ZK_HUF_CTAS)
     bool no_side = false;             // host pipelines: concurrency comes from the other sub-batches; every extra stream costs a hardware queue
+    cudaStream_t up = nullptr, down = nullptr;      // host pipelines: dedicated upload / download streams (not owned); nullptr = everything on `stream`
+    cudaEvent_t ev_up = nullptr, ev_done = nullptr, ev_down = nullptr;
     cudaStream_t side = nullptr; cudaEvent_t ev_scan = nullptr, ev_huf = nullptr;   // Huffman kernel runs beside the FSE kernel
     ZkEntry* h_entries = nullptr; ZkCounters* h_counters = nullptr; uint64_t* h_off = nullptr;   // pinned
     size_t want_blocks = 0, want_lit = 0, want_seq = 0;   // exact needs reported by a batch that overflowed
