@@ -52,11 +52,14 @@ extern "C" {
 #define ZK_ERR_IO (-1004) /* Kind::IO                     */
 #define ZK_ERR_NO_DEVICE (-1005) /* no CUDA device / CUDA failure: the product never falls back to the CPU */
 #define ZK_ERR_INVALID_ARG (-1006)
+#define ZK_ERR_CUDA (-1007) /* a CUDA runtime call or a kernel failed after the context was created; zk_last_cuda_error() has the text */
 /* Kind::Zstd(code): returned as -(ZSTD_ErrorCode), i.e. in [-120, -1] */
 #define ZK_ERR_ZSTD(code) (-(int32_t)(code))
 #define ZK_IS_ZSTD_ERR(rc) ((rc) < 0 && (rc) > -1000)
 
 const char* zk_error_name(int32_t rc);
+/* cudaGetErrorString of the most recent CUDA failure seen by this thread ("" if none) */
+const char* zk_last_cuda_error(void);
 
 /* ------------------------------------------------------------------ context (CCtx/DCtx, encode.rs:130, decode.rs:31) */
 typedef struct zk_ctx zk_ctx;

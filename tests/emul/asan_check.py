@@ -24,7 +24,8 @@ for n, fs in ((0, 100), (1, 100), (15, 100), (16, 16), (31, 100), (100, 100), (1
 rng = np.random.default_rng(3)
 cases.check_compress_roundtrip(ctx, rng.integers(0, 64, 80_000, dtype=np.uint8), 1 << 20, 1, False)      # tiled Huffman packer
 cases.check_range_reads_stop_early(ctx, n=400_000, frame_size=200_000, reads=8)
-cases.check_corruption_is_detected(ctx, trials=8)
+cases.check_corruption_is_detected(ctx, trials=8)          # includes the crafted frames of the round-1 advisory
+cases.check_special_entries(ctx); cases.check_patch_cycle(ctx); cases.check_prefix_batches(ctx, n=120_000)
 cases.check_cycle_tiny_buffers(ctx); cases.check_decoder_state_machine(ctx); cases.check_libzstd_archive_through_decoder(ctx)
 kinds = ["text", "structured", "lowent", "random", "runs"]
 t0 = time.time(); it = 0

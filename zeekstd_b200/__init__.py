@@ -32,6 +32,7 @@ _ERR_OFFSET_OUT_OF_RANGE = -1002
 _ERR_FRAME_INDEX_TOO_LARGE = -1003
 _ERR_IO = -1004
 _ERR_NO_DEVICE = -1005
+_ERR_CUDA = -1007
 
 
 class Error(Exception):
@@ -41,12 +42,17 @@ class Error(Exception):
         self.rc = int(rc)
         lib = lib or _native.default_lib()
         name = lib.zk_error_name(self.rc)
-        super().__init__(f"{name.decode() if name else 'error'}; code {self.rc}")
+        detail = ""
+        if self.rc == _ERR_CUDA:
+            msg = lib.zk_last_cuda_error()
+            detail = f" [{msg.decode()}]" if msg else ""
+        super().__init__(f"{name.decode() if name else 'error'}{detail}; code {self.rc}")
 
     def is_number_conversion_failed(self) -> bool: return self.rc == _ERR_NUMBER_CONVERSION
     def is_offset_out_of_range(self) -> bool: return self.rc == _ERR_OFFSET_OUT_OF_RANGE
     def is_frame_index_too_large(self) -> bool: return self.rc == _ERR_FRAME_INDEX_TOO_LARGE
     def is_io(self) -> bool: return self.rc == _ERR_IO
+    def is_cuda(self) -> bool: return self.rc == _ERR_CUDA
     def is_zstd(self) -> bool: return -1000 < self.rc < 0
     def zstd_code(self) -> int: return -self.rc if self.is_zstd() else 0
 

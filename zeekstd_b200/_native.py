@@ -42,6 +42,7 @@ class Seekable(ctypes.Structure):
 _SIGS = {
     "zk_error_name": (c_char_p, [c_int32]),
     "zk_version": (c_char_p, []),
+    "zk_last_cuda_error": (c_char_p, []),
     "zk_ctx_create": (c_int32, [c_int32, c_uint32, POINTER(c_void_p)]),
     "zk_ctx_destroy": (None, [c_void_p]),
     "zk_ctx_kernel_launches": (c_uint64, [c_void_p]),

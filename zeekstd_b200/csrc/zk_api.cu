@@ -8,8 +8,13 @@
 #include <stdlib.h>
 #include <vector>
 
+static thread_local char zk_tls_cuda_msg[256] = "";
+void zk_note_cuda_error(const char* what, int code) {
+    snprintf(zk_tls_cuda_msg, sizeof zk_tls_cuda_msg, "%s: %s", what, cudaGetErrorString((cudaError_t)code));
+}
+extern "C" const char* zk_last_cuda_error(void) { return zk_tls_cuda_msg; }
 #ifndef ZK_EMUL
-#define ZK_RT_OK(x) do { if ((x) != cudaSuccess) { (void)cudaGetLastError(); return ZK_ERR_NO_DEVICE; } } while (0)
+#define ZK_RT_OK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { zk_note_cuda_error(#x, (int)e__); (void)cudaGetLastError(); return ZK_ERR_CUDA; } } while (0)
 #else
 #define ZK_RT_OK(x) do { (void)(x); } while (0)
 #endif
@@ -45,6 +50,7 @@ extern "C" const char* zk_error_name(int32_t rc) {
     case ZK_ERR_IO: return "io error";
     case ZK_ERR_NO_DEVICE: return "no usable CUDA device (zeekstd_b200 has no CPU fallback)";
     case ZK_ERR_INVALID_ARG: return "invalid argument";
+    case ZK_ERR_CUDA: return "CUDA runtime or kernel failure (see zk_last_cuda_error)";
     // strings of ZSTD_getErrorName for the codes this codec can raise
     case -1: return "Error (generic)";
     case -10: return "Unknown frame descriptor";
@@ -186,7 +192,7 @@ extern "C" int32_t zk_decompress_frames_dev(zk_ctx* c, const void* d_comp, const
         int rc = zk_decode_batch(ws, st, (const uint8_t*)d_comp, c_off + first, d_off + first, end - first, (uint8_t*)d_dst,
                                  verify, status ? status + first : nullptr, (int)zk_env_size("ZK_EXEC_WARPS", 0));
         if (rc && !worst) worst = rc;
-        if (rc == -(int)ZKZ_GENERIC || rc == -(int)ZKZ_MEMORY_ALLOCATION) return rc;
+        if (rc == ZK_INT_CUDA || rc == -(int)ZKZ_MEMORY_ALLOCATION) return rc;
         first = end;
     }
     cudaEventRecord(c->ev1, st);
@@ -379,7 +385,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         if (rc) return rc;
         if (out_pos + produced > dst_cap) return ZK_ERR_ZSTD(ZKZ_DST_TOO_SMALL);
         tr.mark(s.stream, sub_k[si], 3);
-        if (cudaMemcpyAsync(dst + out_pos, s.d_out, produced, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) return ZK_ERR_NO_DEVICE;
+        if (cudaMemcpyAsync(dst + out_pos, s.d_out, produced, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) return ZK_ERR_CUDA;
         tr.mark(s.stream, sub_k[si], 4);
         out_pos += produced;
         return 0;
@@ -394,7 +400,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
             if (err) break;
         }
         ZkSlot& s = c->slot[si]; ZkSubEnc& sb = sub[si];
-        if (cudaStreamSynchronize(s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }   // its previous D2H must be done before d_out is reused
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) { err = ZK_ERR_CUDA; break; }   // its previous D2H must be done before d_out is reused
         sb.f0 = f0; sb.cnt = nf - f0 < per ? nf - f0 : per;
         sb.in_off = (size_t)f0 * frame_size;
         sb.in_len = n - sb.in_off < (size_t)sb.cnt * frame_size ? n - sb.in_off : (size_t)sb.cnt * frame_size;
@@ -402,7 +408,7 @@ extern "C" int32_t zk_compress_frames(zk_ctx* c, const uint8_t* src, size_t n, u
         int rc = zk_slot_ensure(&s, sb.in_len + 32, bound + 32);
         if (rc) { err = rc; break; }
         sub_k[si] = (int)k; tr.mark(s.stream, (int)k, 0);
-        if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_NO_DEVICE; break; }
+        if (sb.in_len && cudaMemcpyAsync(s.d_in, src + sb.in_off, sb.in_len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { err = ZK_ERR_CUDA; break; }
         tr.mark(s.stream, (int)k, 1);
         s.ews.no_side = zk_env_size("ZK_HOST_SIDE", 1) == 0;
         s.ews.prefix = c->cur_prefix_len ? c->d_prefix : nullptr; s.ews.prefix_len = c->cur_prefix_len;

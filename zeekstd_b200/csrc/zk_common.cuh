@@ -21,6 +21,10 @@
 #include <stdint.h>
 #include <stddef.h>
 
+// internal status of a failed CUDA runtime call / kernel (the C ABI's ZK_ERR_CUDA); the text is kept per thread
+#define ZK_INT_CUDA (-1007)
+void zk_note_cuda_error(const char* what, int code);
+
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
 // slots: 0 scan, 1 seq, 2 huf, 3 exec, 4 xxh64(dec), 5 match, 6 entropy-enc, 7 frame assembly
 #define ZK_PROF_SLOTS 8

@@ -300,7 +300,7 @@ __device__ int zk_locate_seq_tables(ZkSeqSlot& sl, const uint8_t* b, uint32_t bs
 
 // Build one sequence decoding table from sl.cnt[t] (A.6).  The symbol spread is written into the cell array itself and
 // converted to cells in place.
-__device__ int zk_build_seq_table(ZkSeqSlot& sl, int t) {
+__device__ int zk_build_seq_table(ZkSeqSlot& sl, int t, uint16_t* nxt_scratch = nullptr) {
     uint32_t* cell = t == 0 ? sl.ll : (t == 1 ? sl.of : sl.ml);
     if (sl.tbl_mode[t] == 1) {
         const uint32_t sy = (uint32_t)sl.cnt[t][0];
@@ -309,7 +309,7 @@ __device__ int zk_build_seq_table(ZkSeqSlot& sl, int t) {
         return 0;
     }
     int log = sl.tbl_log[t], S = 1 << log, nsym = sl.tbl_nsym[t], high = S - 1;
-    uint16_t* nxt = sl.nxt; const int16_t* cnt = sl.cnt[t];
+    uint16_t* nxt = nxt_scratch ? nxt_scratch : sl.nxt; const int16_t* cnt = sl.cnt[t];
     for (int s = 0; s < nsym; s++) {
         if (cnt[s] == -1) { cell[high--] = (uint32_t)s; nxt[s] = 1; }
         else nxt[s] = (uint16_t)cnt[s];
@@ -449,6 +449,7 @@ struct ZkSeq2Chain {
     ZkSeqSlot t;                           // thin cells + build scratch (zk_locate_seq_tables / zk_build_seq_table)
     alignas(128) uint32_t ring[ZK_S2_RING_BYTES / 4];   // staged bitstream (bulk copies want 16-byte aligned shared addresses): byte at offset o from gbase lives at ring byte o & 2047
     uint4 rec[32];                         // per step: {LL cell, OF cell, ML cell, bit cursor before the extra bits}
+    uint16_t nxt2[2][64];                  // build scratch of the OF / ML tables (LL uses t.nxt): the three tables are built side by side
     alignas(8) unsigned long long bar[4];  // one mbarrier per tile slot
     uint32_t lit_end, out_end, r0, r1, r2; // carries of the helper phase
     int st;
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(32) zk_seq2_kernel(ZkDecodeArgs a) {
         uint32_t bidx = 0, remaining = 0, done = 0, cur = 0, sb_bit = 0, s_l = 0, s_o = 0, s_m = 0, seq_base = 0, lit_size = 0;
         const uint8_t* gbase = nullptr;
         int next_issue = -1, next_wait = -1, top_tile = 0; uint32_t stream_end_off = 0, use0 = 0;
-        bool live = false;
+        bool live = false, parsed = false;
         if (chain_lane) {
             ch.st = 0; ch.lit_end = 0; ch.out_end = 0; ch.r0 = ZK_SYM_MAKE(0, 0); ch.r1 = ZK_SYM_MAKE(1, 0); ch.r2 = ZK_SYM_MAKE(2, 0);
             const uint32_t my = first + (uint32_t)myc;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(32) zk_seq2_kernel(ZkDecodeArgs a) {
                     if (!st && blk.ll_ref >= 0) { const ZkBlock& rb = a.blocks[blk.ll_ref]; uint32_t d; st = zk_locate_seq_tables(ch.t, ebase + rb.src, rb.size, true, false, false, &d); }
                     if (!st && blk.of_ref >= 0) { const ZkBlock& rb = a.blocks[blk.of_ref]; uint32_t d; st = zk_locate_seq_tables(ch.t, ebase + rb.src, rb.size, false, true, false, &d); }
                     if (!st && blk.ml_ref >= 0) { const ZkBlock& rb = a.blocks[blk.ml_ref]; uint32_t d; st = zk_locate_seq_tables(ch.t, ebase + rb.src, rb.size, false, false, true, &d); }
-                    for (int t = 0; t < 3 && !st; t++) st = zk_build_seq_table(ch.t, t);
+                    ch.st = st; parsed = !st;
                     const uint8_t* sp = b + bits_off; const uint32_t sn = blk.size - bits_off;
                     if (!st && (sn == 0 || sp[sn - 1] == 0)) st = ZKZ_CORRUPTION;
                     if (!st) {
@@ -526,6 +527,17 @@ __global__ void __launch_bounds__(32) zk_seq2_kernel(ZkDecodeArgs a) {
                 }
             }
         }
+        // ---------------- the three decoding tables of every chain, built side by side by lanes 0..2 of the chain's lane group
+        __syncwarp();
+        {
+            const bool go = __shfl_sync(0xFFFFFFFFu, (uint32_t)(parsed && ch.st == 0), myc * 8) != 0;
+            const int t = lane & 7;
+            int bst = 0;
+            if (go && t < 3) bst = zk_build_seq_table(ch.t, t, t == 0 ? nullptr : ch.nxt2[t - 1]);
+            const uint32_t failed = __ballot_sync(0xFFFFFFFFu, bst != 0);
+            if (chain_lane && ((failed >> (myc * 8)) & 7u) && ch.st == 0) ch.st = ZKZ_CORRUPTION;
+        }
+        __syncwarp();
         // ---------------- tiles of 32 steps
         for (;;) {
             uint32_t cnt = 0;
@@ -1941,7 +1953,7 @@ __global__ void __launch_bounds__(128) zk_xxh64_kernel(ZkDecodeArgs a) {
 // host-side launcher
 // =============================================================================================
 #ifndef ZK_EMUL
-#define ZK_CUDA_OK(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) return -(int)ZKZ_GENERIC; } while (0)
+#define ZK_CUDA_OK(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) { zk_note_cuda_error(#x, (int)err__); return ZK_INT_CUDA; } } while (0)
 #else
 #define ZK_CUDA_OK(x) do { (void)(x); } while (0)
 #endif
@@ -2168,7 +2180,7 @@ int zk_decode_collect(ZkDecodeWs* ws, cudaStream_t stream, int32_t* status_out) 
     if (ws->down && ws->ev_down) ZK_CUDA_OK(cudaEventSynchronize(ws->ev_down));     // recorded by the caller after the output copy on the download stream
     else ZK_CUDA_OK(cudaStreamSynchronize(stream));
 #ifndef ZK_EMUL
-    if (cudaGetLastError() != cudaSuccess) return -(int)ZKZ_GENERIC;
+    { cudaError_t le__ = cudaGetLastError(); if (le__ != cudaSuccess) { zk_note_cuda_error("kernel launch / execution", (int)le__); return ZK_INT_CUDA; } }
 #endif
     ws->pending_n = 0;
 #ifndef ZK_EMUL

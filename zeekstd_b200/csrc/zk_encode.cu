@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(128) zk_frame_gather_kernel(ZkEncodeArgs a) {
 // host-side launcher
 // =============================================================================================
 #ifndef ZK_EMUL
-#define ZKC_CUDA_OK(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) return -(int)ZKZ_GENERIC; } while (0)
+#define ZKC_CUDA_OK(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) { zk_note_cuda_error(#x, (int)err__); return ZK_INT_CUDA; } } while (0)
 #else
 #define ZKC_CUDA_OK(x) do { (void)(x); } while (0)
 #endif
@@ -1232,7 +1232,7 @@ int zk_encode_collect(ZkEncodeWs* ws, cudaStream_t stream, uint32_t* c_sizes, si
     if (nf == 0) { if (dst_len) *dst_len = 0; return 0; }
     ZKC_CUDA_OK(cudaStreamSynchronize(stream));
 #ifndef ZK_EMUL
-    if (cudaGetLastError() != cudaSuccess) return -(int)ZKZ_GENERIC;
+    { cudaError_t le__ = cudaGetLastError(); if (le__ != cudaSuccess) { zk_note_cuda_error("kernel launch / execution", (int)le__); return ZK_INT_CUDA; } }
 #endif
     ws->pending_frames = 0;
     ws->prof.harvest();

@@ -26,7 +26,9 @@ import torch.distributed as dist
 
 from . import _native
 
-CHUNK_BYTES = 512 << 20          # uncompressed bytes per pipeline chunk (whole frames); >= 2 chunks per rank when possible
+CHUNK_BYTES = 1 << 30            # uncompressed bytes per pipeline chunk (whole frames); >= 2 chunks per rank when possible.
+                                 # The codec kernels are bound by per-frame latency, so a chunk costs about the same whatever its size
+                                 # up to ~512 frames (tools/c4_probe.py: 256 MiB chunks run at half the GiB/s of 1 GiB chunks)
 
 
 def frame_ranges(n_frames: int, world: int):
@@ -168,12 +170,13 @@ class Groups:
             try:
                 import os
                 opts = dist.ProcessGroupNCCL.Options()
-                opts.config.max_ctas = int(os.environ.get("ZK_NCCL_MAX_CTAS", "4"))
+                opts.config.max_ctas = int(os.environ.get("ZK_NCCL_MAX_CTAS", "8"))
                 opts.config.min_ctas = 1
             except Exception:
                 opts = None
         self.down = dist.new_group(pg_options=opts) if opts is not None else dist.new_group()
         self.up = dist.new_group(pg_options=opts) if opts is not None else dist.new_group()
+        self.bulk = dist.new_group()          # exchanges nothing overlaps with (the archive gather after compression): full width
 
 
 _groups: Groups | None = None
@@ -279,7 +282,7 @@ def sharded_compress(codec, x_root, n_total: int, frame_size: int, level: int = 
         for r in range(world):
             o0, o1 = int(starts[first[r]]), int(starts[first[r + 1]])
             if o1 > o0 and r != root:
-                ops.append(dist.P2POp(dist.irecv, out[o0:o1], r, g.up))
+                ops.append(dist.P2POp(dist.irecv, out[o0:o1], r, g.bulk))
         reqs = _post(ops)
         o0, o1 = int(starts[first[root]]), int(starts[first[root + 1]])
         out[o0:o1] = local[:pos]
@@ -287,7 +290,7 @@ def sharded_compress(codec, x_root, n_total: int, frame_size: int, level: int = 
         for rr in recv_reqs:
             _wait(rr)
     elif pos:
-        _wait(_post([dist.P2POp(dist.isend, local[:pos], root, g.up)]))
+        _wait(_post([dist.P2POp(dist.isend, local[:pos], root, g.bulk)]))
     if stats is not None:
         t2 = _now(device)
         stats.update(compress_total_ms=(t2 - t0) * 1e3, compress_until_codec_done_ms=(t1 - t0) * 1e3, compress_codec_ms=codec.device_ms,
