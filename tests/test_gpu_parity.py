@@ -48,10 +48,18 @@ def test_decode_frame_size_sweep(ctx):
 
 
 @pytest.mark.parametrize("kind", ["text", "structured", "lowent", "random", "runs"])
-@pytest.mark.parametrize("level,fs,ck", [(1, 2 << 20, False), (3, 512 << 10, True)])
+@pytest.mark.parametrize("level,fs,ck", [(1, 2 << 20, False), (3, 512 << 10, True), (7, 1 << 20, True)])
 def test_compress_roundtrip(ctx, kind, level, fs, ck):
     r = cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 6 << 20, seed=7).numpy(), fs, level, ck)
     assert r >= 0.99
+
+
+def test_compression_levels_are_tiers(ctx):
+    """EncodeOptions::compression_level (encode.rs:176): three tiers here -- 1, 2-3, >= 4 -- each at least as dense as the one below
+    on the reference's corpus"""
+    d = corpus.dickens()[: 8 << 20]
+    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (1, 3, 4)]
+    assert sizes[0] > sizes[1] > sizes[2], sizes
 
 
 def test_compress_edge_sizes(ctx):

@@ -35,7 +35,8 @@ def test_decode_tiny_frames_and_empty(ctx):
 
 
 @pytest.mark.parametrize("kind,level,fs,ck", [("text", 3, 40_000, True), ("text", 1, 11_000, False), ("structured", 3, 40_000, False),
-                                               ("lowent", 3, 40_000, True), ("random", 3, 40_000, True), ("runs", 3, 40_000, True)])
+                                               ("lowent", 3, 40_000, True), ("random", 3, 40_000, True), ("runs", 3, 40_000, True),
+                                               ("text", 5, 40_000, True), ("lowent", 9, 40_000, False), ("structured", 19, 12_000, True)])
 def test_compress_roundtrip(ctx, kind, level, fs, ck):
     cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 40_000, seed=3).numpy(), fs, level, ck)
 

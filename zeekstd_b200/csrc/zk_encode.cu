@@ -74,6 +74,10 @@ template <int HLOG>
 __device__ __forceinline__ uint32_t zkc_hash5(unsigned long long v) {
     return (uint32_t)(((v << 24) * 889523592379ull) >> (64 - HLOG));
 }
+template <int HLOG>
+__device__ __forceinline__ uint32_t zkc_hash8(unsigned long long v) {
+    return (uint32_t)((v * 0xCF1BBCDCB7A56463ull) >> (64 - HLOG));
+}
 
 // =============================================================================================
 // K-C1: match finding.  One warp per block; lane i examines position ip + i * stride.
@@ -100,13 +104,16 @@ __global__ void __launch_bounds__(256) zk_prefix_stage_kernel(ZkEncodeArgs a) {
     for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) d[a.ptail + len + i] = 0;
 }
 
-template <int HLOG>
-__global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArgs a) {
-    __shared__ uint16_t tables[ZKC_C1_WARPS][1 << HLOG];
+// DFAST (level >= 4): a second table indexed by a hash of EIGHT bytes is probed first -- its candidates are long matches by
+// construction, the 5-byte table catches the rest (the idea of zstd's double-fast strategy); two tables of 2^HLOG entries per warp.
+template <int HLOG, int NW, bool DFAST>
+__global__ void __launch_bounds__(NW * 32) zk_match_kernel(ZkEncodeArgs a) {
+    __shared__ uint16_t tables[NW][(DFAST ? 2 : 1) << HLOG];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * ZKC_C1_WARPS + warp;
+    const uint32_t b = blockIdx.x * NW + warp;
     if (b >= a.n_blocks) return;
     uint16_t* table = tables[warp];
+    uint16_t* tableL = table + (1 << HLOG);                // only touched when DFAST
     size_t lo, hi, fstart;
     zkc_block_range(a, b, lo, hi, fstart);
     // history: up to one block of the same frame before `lo` is searchable (positions < 64 KiB fit the u16 table); the first
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
     const size_t base = lo - fstart >= ZKC_BLOCK ? lo - ZKC_BLOCK : fstart;
     const uint8_t* sb = pfx ? a.pstage + (size_t)(b / a.blocks_per_frame) * ZKC_PSLOT : a.src + base;
     const uint32_t lo32 = pfx ? a.ptail : (uint32_t)(lo - base), hi32 = lo32 + (uint32_t)(hi - lo);
-    for (int i = lane; i < (1 << HLOG); i += 32) table[i] = 0;
+    for (int i = lane; i < ((DFAST ? 2 : 1) << HLOG); i += 32) table[i] = 0;
     __syncwarp();
     const uint32_t len = hi32 - lo32;
     uint16_t* o_ll = a.seq_ll + (size_t)b * ZKC_MAXSEQ; uint16_t* o_ml = a.seq_ml + (size_t)b * ZKC_MAXSEQ;
@@ -131,9 +138,15 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
         if (a.level >= 2 || pfx) {
             for (uint32_t p0 = 0; p0 < lo32; p0 += 32) {
                 const uint32_t p = p0 + lane;
-                const uint32_t hh = p < lo32 ? zkc_hash5<HLOG>(zkc_ld8(sb + p)) : (0xFFFF0000u | (uint32_t)lane);
+                const unsigned long long v8 = p < lo32 ? zkc_ld8(sb + p) : 0ull;
+                const uint32_t hh = p < lo32 ? zkc_hash5<HLOG>(v8) : (0xFFFF0000u | (uint32_t)lane);
                 const uint32_t same = __match_any_sync(0xFFFFFFFFu, hh);
                 if (p < lo32 && lane == 31 - __clz((int)same)) table[hh] = (uint16_t)p;
+                if (DFAST) {
+                    const uint32_t hl = p < lo32 ? zkc_hash8<HLOG>(v8) : (0xFFFF0000u | (uint32_t)lane);
+                    const uint32_t sameL = __match_any_sync(0xFFFFFFFFu, hl);
+                    if (p < lo32 && lane == 31 - __clz((int)sameL)) tableL[hl] = (uint16_t)p;
+                }
             }
             __syncwarp();
         }
@@ -157,17 +170,25 @@ __global__ void __launch_bounds__(ZKC_C1_WARPS * 32) zk_match_kernel(ZkEncodeArg
             const unsigned long long cur = zkc_ld8(sb + p);
             const uint32_t h = zkc_hash5<HLOG>(cur);
             const uint32_t cand = table[h];
+            uint32_t hl = 0, candL = 0;
+            if (DFAST) { hl = zkc_hash8<HLOG>(cur); candL = tableL[hl]; }
             __syncwarp();
             // several lanes may hash to the same slot: the highest position wins, as sequential insertion would leave it
             // (keeps the compressed bytes deterministic)
             const uint32_t same = __match_any_sync(0xFFFFFFFFu, h);
             if (lane == 31 - __clz((int)same)) table[h] = (uint16_t)p;
-            // candidate from the hash table, and the repeat-offset candidate
+            if (DFAST) { const uint32_t sameL = __match_any_sync(0xFFFFFFFFu, hl); if (lane == 31 - __clz((int)sameL)) tableL[hl] = (uint16_t)p; }
+            // candidate from the hash table(s), and the repeat-offset candidate
             uint32_t moff = 0, mlen0 = 0;
             if (cand < p) {
                 const unsigned long long x = zkc_ld8(sb + cand) ^ cur;
                 const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
                 if (m >= ZKC_MINMATCH) { moff = p - cand; mlen0 = m; }
+            }
+            if (DFAST && candL < p && candL != cand) {
+                const unsigned long long x = zkc_ld8(sb + candL) ^ cur;
+                const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
+                if (m >= ZKC_MINMATCH && m > mlen0) { moff = p - candL; mlen0 = m; }       // both 8 long: the nearer one (5-byte table) is kept
             }
             if (rep && p >= rep) {
                 const unsigned long long x = zkc_ld8(sb + p - rep) ^ cur;
@@ -1200,8 +1221,11 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
         ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, ss, a);
     }
     ws->prof.begin(5, stream);
-    if (a.level <= 1) ZK_LAUNCH(zk_match_kernel<ZKC_HLOG_FAST>, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
-    else ZK_LAUNCH(zk_match_kernel<ZKC_HLOG>, (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
+    // three tiers (EncodeOptions::compression_level, encode.rs:176): 1 = 2048-entry table, no history, no lazy step; 2-3 = 4096 entries,
+    // previous-block history, one lazy step; >= 4 = double table (8-byte + 5-byte hashes, 4096 entries each), two warps per CTA
+    if (a.level <= 1) ZK_LAUNCH((zk_match_kernel<ZKC_HLOG_FAST, ZKC_C1_WARPS, false>), (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
+    else if (a.level <= 3) ZK_LAUNCH((zk_match_kernel<ZKC_HLOG, ZKC_C1_WARPS, false>), (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
+    else ZK_LAUNCH((zk_match_kernel<ZKC_HLOG, 2, true>), (uint32_t)((n_blocks + 1) / 2), 64, 0, stream, a);
     ws->prof.end(5, stream);
     const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqWarp) * ZKC_SW;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
