@@ -58,12 +58,12 @@ TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic_r2.json")
 
 def workload_c1():
     from zeekstd_b200 import corpus
-    return f"silesia-mix 1 GiB (configs[1]); text = {corpus.text_source()}"
+    return f"silesia-mix {WORKLOAD_BYTES >> 20} MiB (configs[1]); text = {corpus.text_source()}"
 
 
 def workload_c4(nbytes):
     from zeekstd_b200 import corpus
-    return f"mixed-entropy {nbytes >> 30} GiB (configs[3]); text = {corpus.text_source()}"
+    return f"mixed-entropy {nbytes >> 20} MiB (configs[3]); text = {corpus.text_source()}"
 
 
 def peaks():
@@ -153,13 +153,20 @@ def single_thread_note(data: np.ndarray, level: int, checksum: bool):
             "sample": f"{data.size >> 20} MiB", "note": "what zeekstd's own single-threaded Encoder/Decoder reaches"}
 
 
+L2_NOTE = "GPU arm: a 256 MiB buffer is written between timed iterations and the inputs exceed the 126 MB L2"
+EXCHANGE_C4 = ("GPU arm: NCCL inside the timed region -- scatter input -> compress -> all_gather(frame sizes) -> gather archive to root; "
+               "scatter archive -> decompress -> gather output to root (chunked, pipelined, two communicators)")
+
+
 def config_c1(n):
-    return {"workload": workload_c1(), "frame_size": FRAME, "level": LEVEL, "checksum": False, "bytes_per_gpu": n, "step": "compress+decompress"}
+    """the SAME dict in both arms (the driver compares them)"""
+    return {"workload": workload_c1(), "frame_size": FRAME, "level": LEVEL, "checksum": False, "bytes_per_gpu": n, "step": "compress+decompress",
+            "l2": L2_NOTE, "exchange": "none"}
 
 
 def config_c4(nbytes, world):
     return {"workload": workload_c4(nbytes), "frame_size": FRAME, "level": C4_LEVEL, "checksum": True, "bytes_total": nbytes, "step": "compress+decompress",
-            "parallelism": f"frames sharded over {world} GPUs, root-held buffer"}
+            "parallelism": f"frames sharded over {world} GPUs, root-held buffer", "l2": L2_NOTE, "exchange": EXCHANGE_C4}
 
 
 # ================================================================================================ reference arm
@@ -383,7 +390,7 @@ def main_ours(args, rank, world, local, ncores):
         torch.cuda.empty_cache()
         line = {"metric": METRIC, "value": round(weak_value, 3), "unit": "GiB/s", "n_gpus": 1, "steps": K, "warmup": W,
                 "ms_per_step": round(tc_ms + td_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": dict(config_c1(n), l2="256 MiB buffer written between timed iterations; inputs (1 GiB) exceed L2", exchange="none"),
+                "config": config_c1(n),
                 "statistic": "mean over the timed steps",
                 "compress_GiBps": round(n / gib / (tc_ms / 1e3), 3), "decompress_GiBps": round(n / gib / (td_ms / 1e3), 3),
                 "ratio": round(n / clen, 4), "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "config4_one_gpu": c4,
@@ -394,7 +401,7 @@ def main_ours(args, rank, world, local, ncores):
     # ---------------------------------------------------------------- N > 1: configs[3], strong scaling, exchange inside the timed region
     from zeekstd_b200 import parallel
     weak = {"value": round(weak_value, 3), "unit": "GiB/s", "scaling": "weak", "compress_GiBps": round(world * n / gib / (tc_ms / 1e3), 3),
-            "decompress_GiBps": round(world * n / gib / (td_ms / 1e3), 3), "config": dict(config_c1(n), exchange="none (every rank its own buffer)")}
+            "decompress_GiBps": round(world * n / gib / (td_ms / 1e3), 3), "config": config_c1(n)}
     del x
     torch.cuda.empty_cache()
     nb = C4_BYTES
@@ -468,9 +475,7 @@ def main_ours(args, rank, world, local, ncores):
     sample = xr[: min(nb, C4_REF_BYTES // 2)].cpu().numpy()
     line = {"metric": METRIC, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(c_ms + d_ms, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": dict(config_c4(nb, world), l2="256 MiB buffer written between timed iterations; inputs exceed L2",
-                           exchange="NCCL inside the timed region: scatter input -> compress -> all_gather(frame sizes) -> gather archive to root; "
-                                    "scatter archive -> decompress -> gather output to root (chunked, pipelined, two communicators)"),
+            "config": config_c4(nb, world),
             "statistic": "mean over the timed steps; device time (CUDA events), max over ranks",
             "compress_GiBps": round(nb / gib / (c_ms / 1e3), 3), "decompress_GiBps": round(nb / gib / (d_ms / 1e3), 3), "ratio": round(nb / clen4, 4),
             "per_rank": per_rank, "limiting": limiting, "one_gpu_same_workload": one_gpu, "weak": weak,
