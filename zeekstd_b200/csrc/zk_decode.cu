@@ -1266,8 +1266,8 @@ __device__ __forceinline__ void zk_exec_body(ZkD2Smem& sm, const ZkDecodeArgs& a
                 continue;
             }
             // ---------------- 32 sequences, one per lane
-#ifndef ZK_EMUL
-#define ZK_STAMP(k) do { if (a.trace && e == 0 && c < 1024 && lane == 0) a.trace[c * 8 + (k)] = clock64(); } while (0)
+#if !defined(ZK_EMUL) && defined(ZK_EXEC_TRACE_BUILD)       // per-chunk clock64 stamps of entry 0 (tools/exec_trace.py): a debug build only --
+#define ZK_STAMP(k) do { if (a.trace && e == 0 && c < 1024 && lane == 0) a.trace[c * 8 + (k)] = clock64(); } while (0)   // the checks were 3 % of the kernel's instructions
 #else
 #define ZK_STAMP(k) do { } while (0)
 #endif
