@@ -1176,10 +1176,14 @@ __device__ __forceinline__ bool zk_d2_wait_start(ZkD2Smem& sm, uint32_t c, uint3
     for (;;) {
         uint32_t ok = 0, ab = 0;
         if (lane == 0) {
-            zk_d2_help(sm);
             ab = *(volatile int*)&sm.abort_code != 0;
-            const uint32_t fc = ZK_VOL(sm.flushed_chunk), fp = ZK_VOL(sm.flushed_pos);
+            uint32_t fc = ZK_VOL(sm.flushed_chunk), fp = ZK_VOL(sm.flushed_pos);
             ok = exclusive ? (fc == c) : (fc == c || (end_pos - fp <= window && c - fc < ZK_D2_META - 2));
+            if (!ok) {           // only then is it worth walking the flags (the walk was 6 % of the kernel's instructions when done on every entry)
+                zk_d2_help(sm);
+                fc = ZK_VOL(sm.flushed_chunk); fp = ZK_VOL(sm.flushed_pos);
+                ok = exclusive ? (fc == c) : (fc == c || (end_pos - fp <= window && c - fc < ZK_D2_META - 2));
+            }
             __threadfence_block();
         }
         ok = __shfl_sync(0xFFFFFFFFu, ok, 0); ab = __shfl_sync(0xFFFFFFFFu, ab, 0);
