@@ -2144,7 +2144,7 @@ int zk_decode_enqueue(ZkDecodeWs* ws, cudaStream_t stream, const uint8_t* d_comp
         // second-generation kernel: <= 64 registers, so 32 warps per SM whatever the split; ring = what is left of the
         // SM's shared memory per resident entry
         if (per_sm > 8) per_sm = 8;
-        if (W <= 0) W = 32 / per_sm;
+        if (W <= 0) W = 16 / per_sm;        // measured (profiles/README.md): more warps per frame than this make the in-order chain SLOWER
         if (W > 32) W = 32;
         if (W < 2) W = 2;
         uint32_t ring = 128 * 1024;
