@@ -347,7 +347,8 @@ def main_ours(args, rank, world, local, ncores):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))   # a hang must fail fast
     rig = Rig(local)
     lib, ctx, dev = rig.lib, rig.ctx, rig.dev
     W, K = max(args.warmup, 3), max(args.steps, 1)
@@ -400,6 +401,7 @@ def main_ours(args, rank, world, local, ncores):
 
     # ---------------------------------------------------------------- N > 1: configs[3], strong scaling, exchange inside the timed region
     from zeekstd_b200 import parallel
+    parallel.groups(dev)                       # creates AND exercises the communicators before anything is in flight
     weak = {"value": round(weak_value, 3), "unit": "GiB/s", "scaling": "weak", "compress_GiBps": round(world * n / gib / (tc_ms / 1e3), 3),
             "decompress_GiBps": round(world * n / gib / (td_ms / 1e3), 3), "config": config_c1(n)}
     del x
@@ -497,7 +499,16 @@ def main():
     ncores = os.cpu_count() or 1
     if args.impl == "reference":
         return main_reference(args, rank, world, ncores)
-    return main_ours(args, rank, world, local, ncores)
+    try:
+        return main_ours(args, rank, world, local, ncores)
+    except BaseException:
+        # under torchrun a rank that raises must take the job down NOW: its peers sit in exchanges only it can complete
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(1)
+        raise
 
 
 if __name__ == "__main__":

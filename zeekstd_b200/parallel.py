@@ -162,7 +162,7 @@ class Groups:
     """two communicators: `down` carries root -> ranks traffic, `up` carries ranks -> root traffic, so that the two
     directions of a step never queue behind each other (one NCCL communicator executes its operations in order)"""
 
-    def __init__(self):
+    def __init__(self, device=None):
         opts = None
         if dist.get_backend() == "nccl":
             # The exchange needs a small fraction of NVLink (16 GiB per ~0.3 s step); its kernels must not take SMs from the
@@ -177,15 +177,37 @@ class Groups:
         self.down = dist.new_group(pg_options=opts) if opts is not None else dist.new_group()
         self.up = dist.new_group(pg_options=opts) if opts is not None else dist.new_group()
         self.bulk = dist.new_group()          # exchanges nothing overlaps with (the archive gather after compression): full width
+        # NCCL creates a communicator at its FIRST use, collectively, with device-wide synchronisation inside.  If that first use
+        # falls into a pass where receives posted ahead are already spinning on the GPU, the ranks deadlock (seen at N = 2: the
+        # root sat in the creation of `up` waiting for a rank whose creation waited for a receive only the root could feed).
+        # So every communicator does a collective and a point-to-point round trip in both directions NOW, while nothing is in flight.
+        if device is not None and dist.get_backend() == "nccl":
+            rank, world = dist.get_rank(), dist.get_world_size()
+            for g in (self.down, self.up, self.bulk):
+                t = torch.zeros(16, dtype=torch.uint8, device=device)
+                dist.all_reduce(t, group=g)
+                for root in range(world):
+                    ops = []
+                    if rank == root:
+                        for r in range(world):
+                            if r != root:
+                                ops += [dist.P2POp(dist.isend, t, r, g), dist.P2POp(dist.irecv, torch.empty_like(t), r, g)]
+                    else:
+                        ops = [dist.P2POp(dist.irecv, torch.empty_like(t), root, g), dist.P2POp(dist.isend, t, root, g)]
+                    if ops:
+                        for q in dist.batch_isend_irecv(ops):
+                            q.wait()
+                torch.cuda.synchronize(device)
+            dist.barrier()
 
 
 _groups: Groups | None = None
 
 
-def groups() -> Groups:
+def groups(device=None) -> Groups:
     global _groups
     if _groups is None:
-        _groups = Groups()
+        _groups = Groups(device)
     return _groups
 
 
@@ -216,7 +238,7 @@ def sharded_compress(codec, x_root, n_total: int, frame_size: int, level: int = 
     """x_root: the whole input on the root (a tensor with codec.PAD bytes of slack behind n_total), None elsewhere.
     -> on root: (frames tensor, c_sizes, d_sizes) for the WHOLE input; on other ranks: (None, c_sizes, d_sizes)"""
     rank, world = dist.get_rank(), dist.get_world_size()
-    g = groups()
+    g = groups(device)
     t0 = _now(device) if stats is not None else 0.0
     n_frames = max(1, -(-n_total // frame_size))
     ranges = frame_ranges(n_frames, world)
@@ -305,7 +327,7 @@ def sharded_decompress(codec, comp_root, c_sizes, d_sizes, verify: bool = True, 
     """c_sizes / d_sizes known on every rank (the seek table); comp_root: the archive on the root (PAD bytes of slack).
     -> on root: the decompressed tensor"""
     rank, world = dist.get_rank(), dist.get_world_size()
-    g = groups()
+    g = groups(device)
     t0 = _now(device) if stats is not None else 0.0
     n_frames = len(c_sizes)
     c_off = np.concatenate([[0], np.cumsum(c_sizes)]).astype(np.int64); d_off = np.concatenate([[0], np.cumsum(d_sizes)]).astype(np.int64)
