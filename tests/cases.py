@@ -768,3 +768,189 @@ def check_seek_table(lib):
                 assert e.is_offset_out_of_range()
             else:
                 assert e.is_zstd() and e.zstd_code() == int(pred[4:])
+
+
+# ---------------------------------------------------------------------------------- CLI front end (cli/tests/integration/main.rs)
+def _cli(ctx, argv, stdin: bytes = b""):
+    """run zeekstd_b200.cli.main in-process with ctx as the default context; -> (rc, stdout bytes, stderr text)"""
+    import contextlib
+    import io
+    import sys
+    import zeekstd_b200 as zk
+    from zeekstd_b200 import cli
+
+    class _Std:
+        def __init__(self, data=b""):
+            self.buffer = io.BytesIO(data)
+            self.text = io.StringIO()
+        def isatty(self): return False
+        def write(self, s): return self.text.write(s)
+        def flush(self): pass
+        def readline(self): return self.buffer.readline().decode()
+
+    old_ctx = zk._default_ctx
+    zk.set_default_context(ctx)
+    so, se, si = _Std(), _Std(), _Std(stdin)
+    old = sys.stdout, sys.stderr, sys.stdin
+    sys.stdout, sys.stderr, sys.stdin = so, se, si
+    try:
+        try:
+            rc = cli.main([str(a) for a in argv])
+        except SystemExit as e:
+            rc = int(e.code or 0)
+    finally:
+        sys.stdout, sys.stderr, sys.stdin = old
+        zk.set_default_context(old_ctx)
+    return rc, so.buffer.getvalue() + so.text.getvalue().encode(), se.text.getvalue()
+
+
+def check_cli(ctx, tmp, data: bytes, frame_sizes, tag=""):
+    """one body per test of cli/tests/integration/main.rs, on `data` instead of the whole corpus where sizes must stay small"""
+    import os
+    import zeekstd_b200 as zk
+    from zeekstd_b200 import cli
+    tmp = str(tmp)
+    src = os.path.join(tmp, f"input{tag}.txt")
+    with open(src, "wb") as f:
+        f.write(data)
+
+    # args.rs:331-435 value parsers
+    assert cli.byte_value("10") == 10
+    for s, v in (("10B", 10), ("10 B", 10), ("10K", 10240), ("10 kib", 10240), ("10   mib", 10 << 20), ("2G", 2 << 30), ("2 gib", 2 << 30)):
+        assert cli.byte_value(s) == v, s
+    for bad in ("10 X", " ", "abc B"):
+        try:
+            cli.byte_value(bad); raise AssertionError(bad)
+        except Exception as e:
+            assert not isinstance(e, AssertionError)
+    for s in ("end", "End", "eND", "END"):
+        assert cli.last_frame(s) == "end" and cli.offset_limit(s) is None
+    assert cli.last_frame("7") == 7 and cli.offset_limit("3K") == 3072
+    assert cli.human_bytes(1023) == "1023 B" and cli.human_bytes(10192446) == "9.72 MiB"
+
+    for fs in frame_sizes:
+        # cycle: file -> file -> file (:38-59)
+        z = os.path.join(tmp, f"c{tag}_{fs}.zst")
+        rc, _, err = _cli(ctx, ["compress", src, "--output-file", z, "--frame-size", fs], b"y")
+        assert rc == 0, err
+        back = os.path.join(tmp, f"back{tag}_{fs}")
+        rc, _, err = _cli(ctx, ["decompress", z, "--output-file", back], b"y")
+        assert rc == 0, err
+        assert open(back, "rb").read() == data
+        # what the CLI wrote is a seekable archive libzstd accepts
+        arc = open(z, "rb").read()
+        st = zk.SeekTable.from_bytes(arc)
+        assert st.size_decomp() == len(data) and st.size_comp() + st.into_serializer().encoded_len() == len(arc)
+        # stdin -> file (:61-76), file -> stdout (:78-97), stdin -> stdout (:99-117)
+        z2 = os.path.join(tmp, f"s{tag}_{fs}.zst")
+        rc, _, err = _cli(ctx, ["compress", "--output-file", z2, "--frame-size", fs], data)
+        assert rc == 0 and open(z2, "rb").read() == arc, err
+        rc, out, err = _cli(ctx, ["compress", src, "--stdout", "--frame-size", fs])
+        assert rc == 0 and out == arc, err
+        rc, out, err = _cli(ctx, ["--stdout", "--frame-size", fs], data)          # no sub-command = compress (main.rs:27-30)
+        assert rc == 0 and out == arc, err
+        rc, out, err = _cli(ctx, ["d", z, "-c"])
+        assert rc == 0 and out == data, err
+        # separate seek table (:119-153)
+        z3, t3 = os.path.join(tmp, f"h{tag}_{fs}.zst"), os.path.join(tmp, f"h{tag}_{fs}.table")
+        rc, _, err = _cli(ctx, ["compress", src, "--output-file", z3, "--frame-size", fs, "--seek-table-file", t3], b"y")
+        assert rc == 0, err
+        assert open(z3, "rb").read() == arc[:st.size_comp()]
+        rc, out, err = _cli(ctx, ["decompress", z3, "--seek-table-file", t3, "-c"])
+        assert rc == 0 and out == data, err
+        rc, out, err = _cli(ctx, ["list", t3, "--seek-table-format", "head"])
+        assert rc == 0 and out.count(b"\n") == 2, err
+
+    # output name derivation (:189-290)
+    one = os.path.join(tmp, f"name{tag}.bin")
+    with open(one, "wb") as f:
+        f.write(data[:1000])
+    rc, _, err = _cli(ctx, ["compress", one], b"y")
+    assert rc == 0 and os.path.exists(one + ".zst"), err
+    os.remove(one)
+    rc, _, err = _cli(ctx, ["decompress", one + ".zst"], b"y")
+    assert rc == 0 and open(one, "rb").read() == data[:1000], err
+    noext = os.path.join(tmp, f"noext{tag}")
+    os.rename(one + ".zst", noext)
+    rc, _, err = _cli(ctx, ["decompress", noext])
+    assert rc != 0 and "unknown extension" in err
+    other = noext + ".foo"
+    os.rename(noext, other)
+    rc, _, err = _cli(ctx, ["decompress", other])
+    assert rc != 0 and "unknown extension" in err
+    given = os.path.join(tmp, f"given{tag}.out")
+    rc, _, err = _cli(ctx, ["decompress", other, "--output-file", given])
+    assert rc == 0 and open(given, "rb").read() == data[:1000], err
+
+    # overwrite rules (:292-361): prompt answered "n", stdin input never overwrites, --force does
+    keep = open(given, "rb").read()
+    rc, _, err = _cli(ctx, ["compress", src, "--output-file", given], b"n\n")
+    assert rc != 0 and open(given, "rb").read() == keep
+    rc, _, err = _cli(ctx, ["compress", "--output-file", given], data)
+    assert rc != 0 and "not overwritten" in err and open(given, "rb").read() == keep
+    rc, _, err = _cli(ctx, ["compress", src, "--output-file", given, "--quiet"])
+    assert rc != 0 and open(given, "rb").read() == keep
+    tab = os.path.join(tmp, f"exists{tag}.table")
+    open(tab, "wb").write(b"x")
+    fresh = os.path.join(tmp, f"fresh{tag}.zst")
+    rc, _, err = _cli(ctx, ["compress", "--output-file", fresh, "--seek-table-file", tab], data)
+    assert rc != 0 and open(tab, "rb").read() == b"x" and not os.path.exists(fresh), err
+    rc, _, err = _cli(ctx, ["compress", src, "--output-file", given, "--force"])
+    assert rc == 0 and open(given, "rb").read() != keep, err
+    rc, _, err = _cli(ctx, ["compress", "--output-file", given, "--force"], data)
+    assert rc == 0, err
+    # a missing input creates nothing (:363-377)
+    nothing = os.path.join(tmp, f"nothing{tag}.zst")
+    rc, _, err = _cli(ctx, ["compress", os.path.join(tmp, "does-not-exist"), "--output-file", nothing])
+    assert rc != 0 and not os.path.exists(nothing)
+
+    # frame / offset selection (:379-520)
+    n = len(data)
+    fs6 = n // 6
+    z6 = os.path.join(tmp, f"six{tag}.zst")
+    assert _cli(ctx, ["compress", src, "-o", z6, "-s", fs6], b"y")[0] == 0
+    rc, first, err = _cli(ctx, ["decompress", z6, "-c", "--from-frame", 0, "--to-frame", 0])
+    assert rc == 0 and len(first) == fs6, err
+    rc, rest, err = _cli(ctx, ["decompress", z6, "-c", "--from-frame", 1, "--to-frame", "end"])
+    assert rc == 0 and first + rest == data, err
+    t6 = os.path.join(tmp, f"six{tag}.table")
+    assert _cli(ctx, ["compress", src, "-s", fs6, "-o", z6, "--seek-table-file", t6, "--force"])[0] == 0
+    rc, first, err = _cli(ctx, ["decompress", z6, "--seek-table-file", t6, "-c", "--from-frame", 0, "--to-frame", 0])
+    assert rc == 0 and first == data[:fs6], err
+    zall = os.path.join(tmp, f"all{tag}.zst")
+    assert _cli(ctx, ["compress", src, "-o", zall, "-s", n], b"y")[0] == 0
+    assert _cli(ctx, ["decompress", zall, "-c", "--from-frame", 1])[0] != 0
+    assert _cli(ctx, ["decompress", zall, "-c", "--from-frame", 0, "--to-frame", 1])[0] != 0
+    fs9 = n // 9
+    z9 = os.path.join(tmp, f"nine{tag}.zst")
+    assert _cli(ctx, ["compress", src, "-o", z9, "-s", fs9], b"y")[0] == 0
+    lo, hi = fs9 + fs9 // 2, 4 * fs9 + fs9 // 2
+    rc, out, err = _cli(ctx, ["decompress", z9, "-c", "--from", lo, "--to", hi])
+    assert rc == 0 and out == data[lo:hi], err
+
+    # list (:522-590): summary = 2 lines, --detail = header + one line per frame
+    fs14 = n // 14
+    z14 = os.path.join(tmp, f"fourteen{tag}.zst")
+    assert _cli(ctx, ["compress", src, "-o", z14, "-s", fs14], b"y")[0] == 0
+    frames = -(-n // fs14)
+    rc, out, err = _cli(ctx, ["list", z14])
+    assert rc == 0 and out.count(b"\n") == 2 and out.split(b"\n")[1].split()[0] == str(frames).encode(), err
+    rc, out, err = _cli(ctx, ["list", "--detail", z14])
+    assert rc == 0 and out.count(b"\n") == frames + 1, err
+    rc, out, err = _cli(ctx, ["-r", "list", z14, "--from-frame", 2, "--num-frames", 3])
+    rows = out.decode().splitlines()
+    assert rc == 0 and len(rows) == 4 and [r.split()[0] for r in rows[1:]] == ["2", "3", "4"] and rows[1].split()[2] == str(fs14), err
+    assert _cli(ctx, ["list", z14, "--from-frame", 5, "--to-frame", 2])[0] != 0
+
+    # patch mode (--patch-from / --patch-apply, command.rs:199-263 + compress.rs:32-38)
+    old_v, new_v = data[: n // 2], data[n // 8: n // 2 + n // 8]
+    pf, nf = os.path.join(tmp, f"old{tag}"), os.path.join(tmp, f"new{tag}")
+    open(pf, "wb").write(old_v); open(nf, "wb").write(new_v)
+    zp, zn = os.path.join(tmp, f"patch{tag}.zst"), os.path.join(tmp, f"nopatch{tag}.zst")
+    assert _cli(ctx, ["compress", nf, "-o", zp, "--patch-from", pf, "-s", len(new_v)])[0] == 0
+    assert _cli(ctx, ["compress", nf, "-o", zn, "-s", len(new_v)])[0] == 0
+    rc, out, err = _cli(ctx, ["decompress", zp, "-c", "--patch-apply", pf])
+    assert rc == 0 and out == new_v, err
+    rc, out, err = _cli(ctx, ["decompress", zp, "-c", "--patch-apply", pf, "--mmap-prefix"])
+    assert rc == 0 and out == new_v, err
+    return os.path.getsize(zp), os.path.getsize(zn)

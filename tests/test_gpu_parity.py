@@ -152,6 +152,34 @@ def test_config1_dickens(ctx):
         assert r > 2.0
 
 
+def test_cli_front_end(ctx, tmp_path):
+    """cli/tests/integration/main.rs: the reference's FRAME_SIZES ("10", "123", "3K", "2M", "1G") -- the whole corpus for the
+    sizes that give a sane frame count, a 200 000-byte slice for the two tiny ones; plus a subprocess run of `python -m`"""
+    d = corpus.dickens().tobytes()
+    with_p, without = cases.check_cli(ctx, tmp_path, d, ["3K", "2M", "1G"], tag="full")
+    assert with_p < without * 0.6                       # the patch really uses the prefix (new = old shifted by 1/8)
+    cases.check_cli(ctx, tmp_path, d[1_000_000:1_200_000], ["10", "123"], tag="small")
+    import subprocess
+    import sys
+    src, z = tmp_path / "sub.txt", tmp_path / "sub.txt.zst"
+    src.write_bytes(d[:3_000_000])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "zeekstd_b200", str(src), "-q"], cwd=root, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([sys.executable, "-m", "zeekstd_b200", "decompress", str(z), "-c", "--from", "1M", "--to", "2M"], cwd=root, capture_output=True, timeout=600)
+    assert r.returncode == 0 and r.stdout == d[1 << 20: 2 << 20], r.stderr
+    arc = np.frombuffer(z.read_bytes(), dtype=np.uint8)
+    st = zk.SeekTable.from_bytes(arc)
+    cs, ds = _table_sizes(st)
+    out, sizes = O.ref_decompress_frames(arc[: st.size_comp()], offsets(cs), offsets(ds), threads=8)     # libzstd reads what the CLI wrote
+    assert list(sizes) == ds and out[: 3_000_000].tobytes() == d[:3_000_000]
+
+
+def _table_sizes(st):
+    n = st.num_frames()
+    return [st.frame_size_comp(i) for i in range(n)], [st.frame_size_decomp(i) for i in range(n)]
+
+
 def test_api_encode_side(ctx):
     cases.check_cycle_tiny_buffers(ctx)
     cases.check_cycle_tiny_buffers(ctx, zk.FrameSizePolicy.Uncompressed(777))

@@ -138,6 +138,13 @@ def test_range_reads_stop_early(ctx):
     cases.check_range_reads_stop_early(ctx)
 
 
+def test_cli_front_end(ctx, tmp_path):
+    """cli/tests/integration/main.rs on emulator-sized inputs"""
+    from zeekstd_b200 import corpus
+    data = corpus.as_numpy(corpus.make_class("text", 6000, seed=5)).tobytes()
+    cases.check_cli(ctx, tmp_path, data, ["123", "3K", "2M"])
+
+
 def test_zz_decoder_coverage_matrix(ctx):
     """runs last in this file: every cell of SURVEY.md 8a's matrix that fits emulator-sized inputs was decoded above"""
     cases.check_coverage_matrix([c for c in cases.MATRIX_CELLS if c not in ("frames_over_2MiB", "offsets_over_1MiB")])
