@@ -943,7 +943,8 @@ def check_cli(ctx, tmp, data: bytes, frame_sizes, tag=""):
     assert _cli(ctx, ["list", z14, "--from-frame", 5, "--to-frame", 2])[0] != 0
 
     # patch mode (--patch-from / --patch-apply, command.rs:199-263 + compress.rs:32-38)
-    old_v, new_v = data[: n // 2], data[n // 8: n // 2 + n // 8]
+    m = min(n // 2, 48_000)              # new = old shifted by m/4: every match into the prefix is 3m/4 <= 36 000 bytes back, inside the
+    old_v, new_v = data[:m], data[m // 4: m + m // 4]      # 64 KiB match window of these kernels
     pf, nf = os.path.join(tmp, f"old{tag}"), os.path.join(tmp, f"new{tag}")
     open(pf, "wb").write(old_v); open(nf, "wb").write(new_v)
     zp, zn = os.path.join(tmp, f"patch{tag}.zst"), os.path.join(tmp, f"nopatch{tag}.zst")

@@ -142,7 +142,8 @@ def test_cli_front_end(ctx, tmp_path):
     """cli/tests/integration/main.rs on emulator-sized inputs"""
     from zeekstd_b200 import corpus
     data = corpus.as_numpy(corpus.make_class("text", 6000, seed=5)).tobytes()
-    cases.check_cli(ctx, tmp_path, data, ["123", "3K", "2M"])
+    with_p, without = cases.check_cli(ctx, tmp_path, data, ["123", "3K", "2M"])
+    assert with_p < without * 0.7        # --patch-from: 3/4 of the new version is in the prefix
 
 
 def test_zz_decoder_coverage_matrix(ctx):
