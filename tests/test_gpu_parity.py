@@ -166,7 +166,7 @@ def test_cli_front_end(ctx, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "zeekstd_b200", str(src), "-q"], cwd=root, capture_output=True, timeout=600)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([sys.executable, "-m", "zeekstd_b200", "decompress", str(z), "-c", "--from", "1M", "--to", "2M"], cwd=root, capture_output=True, timeout=600)
+    r = subprocess.run([sys.executable, "-m", "zeekstd_b200", "decompress", str(z), "-c", "--from", str(1 << 20), "--to", "2M"], cwd=root, capture_output=True, timeout=600)
     assert r.returncode == 0 and r.stdout == d[1 << 20: 2 << 20], r.stderr
     arc = np.frombuffer(z.read_bytes(), dtype=np.uint8)
     st = zk.SeekTable.from_bytes(arc)

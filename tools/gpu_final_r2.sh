@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 what="${@:-tests bench ncu seek}"
 for w in $what; do case $w in
-tests) (time timeout 600 python -m pytest tests -m gpu -x -q --timeout=150 2>&1 | tail -4) > gpurun_out/r2_final_tests.log 2>&1; cat gpurun_out/r2_final_tests.log;;
+tests) (time timeout 600 python -m pytest tests -m gpu -q --timeout=150 2>&1 | tail -4) > gpurun_out/r2_final_tests.log 2>&1; cat gpurun_out/r2_final_tests.log;;
 bench)
   python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_r2_reference_arm.json
   python bench.py 2> gpurun_out/bench_r2_n1.err | tail -1 > gpurun_out/bench_r2_n1.json
