@@ -955,3 +955,151 @@ def check_cli(ctx, tmp, data: bytes, frame_sizes, tag=""):
     rc, out, err = _cli(ctx, ["decompress", zp, "-c", "--patch-apply", pf, "--mmap-prefix"])
     assert rc == 0 and out == new_v, err
     return os.path.getsize(zp), os.path.getsize(zn)
+
+
+def check_seek_table_fuzz(lib, iters: int = 3000, seed: int = 5):
+    """mutated seek tables (both formats): the native parser and the restatement of seek_table.rs:144-225, 379-436 agree on
+    accept / reject, on the zstd error code, and on every offset of an accepted table"""
+    rng = np.random.default_rng(seed)
+    parsed = rejected = 0
+    for _ in range(iters):
+        t = O.OracleSeekTable()
+        for _ in range(int(rng.integers(0, 12))):
+            t.log_frame(int(rng.integers(0, 1 << 20)), int(rng.integers(0, 1 << 22)))
+        fmt = "head" if rng.integers(2) else "foot"
+        b = bytearray(t.serialize(fmt))
+        lead = bytes(rng.integers(0, 256, int(rng.integers(0, 20)), dtype=np.uint8)) if fmt == "foot" else b""
+        for _ in range(int(rng.integers(0, 3))):
+            k = int(rng.integers(4)); p = int(rng.integers(len(b)))
+            if k == 0: b[p] ^= 1 << int(rng.integers(8))
+            elif k == 1: b[p] = int(rng.integers(256))
+            elif k == 2: del b[p:p + int(rng.integers(1, 5))]
+            else: b[p:p] = bytes(rng.integers(0, 256, int(rng.integers(1, 5)), dtype=np.uint8))
+        blob = lead + bytes(b)
+        try:
+            want, wexc = O.OracleSeekTable.parse(blob, fmt), None
+        except Exception as e:
+            want, wexc = None, e
+        try:
+            got, gexc = zk.SeekTable.from_bytes(blob, zk.Format.Head if fmt == "head" else zk.Format.Foot, lib), None
+        except zk.Error as e:
+            got, gexc = None, e
+        assert (want is None) == (got is None), (fmt, blob.hex(), repr(wexc), repr(gexc))
+        if want is not None:
+            n = want.num_frames()
+            assert got.num_frames() == n
+            for i in range(n):
+                assert got.frame_end_comp(i) == want.c[i + 1] and got.frame_end_decomp(i) == want.d[i + 1], (i, blob.hex())
+            parsed += 1
+        else:
+            if isinstance(wexc, O.ZstdError):
+                assert gexc.is_zstd() and gexc.zstd_code() == wexc.code, (repr(wexc), gexc.rc, blob.hex())
+            rejected += 1
+    assert parsed > iters // 4 and rejected > iters // 4
+
+
+def check_decoder_random_ops(ctx, ops: int = 250, seed: int = 3, n: int = 24_000, frame_size: int = 1_700):
+    """differential test of the Decoder's state machine against the contract of decode.rs:201-270, 344-445, 545-579 written as a
+    model over the plain bytes: a call returns data[offset : min(offset + len(buf), limit)] and advances the offset; offsets and
+    limits beyond size_decomp and frame indices beyond the table are errors that change nothing; reset restores (0, size_decomp).
+    The archive is libzstd-written (ragged last frame), read through a file-like source."""
+    import io
+    rng = np.random.default_rng(seed)
+    data = corpus.as_numpy(corpus.make_mix(n, seed=seed, mix=corpus.CLASS_MIX_MIXED, segment=4096)).tobytes()
+    arc, _ = O.ref_seekable_archive(np.frombuffer(data, dtype=np.uint8), frame_size, 3, True)
+    dec = zk.Decoder(zk.DecodeOptions(io.BytesIO(arc), ctx))
+    total, nf = len(data), dec.seek_table().num_frames()
+    assert dec.seek_table().size_decomp() == total and nf == -(-total // frame_size)
+    off, lim = 0, total
+    fstart = lambda i: min(i * frame_size, total)
+
+    def expect_err(fn, pred):
+        try:
+            fn()
+        except zk.Error as e:
+            assert pred(e), e.rc
+            return
+        raise AssertionError("no error")
+
+    for _ in range(ops):
+        k = int(rng.integers(10))
+        if k <= 3:                                            # decompress
+            ln = int(rng.choice([0, 1, 7, 100, 1699, 1700, 1701, 5000, total]))
+            buf = bytearray(ln)
+            got = dec.decompress(buf)
+            want = data[off: min(off + ln, lim)] if lim > off else b""
+            assert got == len(want) and bytes(buf[:got]) == want, (off, lim, ln, got, len(want))
+            off += got
+        elif k == 4:
+            o = int(rng.integers(0, total + 1)) if rng.integers(8) else total + int(rng.integers(1, 50))
+            if o > total: expect_err(lambda: dec.set_offset(o), lambda e: e.is_offset_out_of_range())
+            else: dec.set_offset(o); off = o
+        elif k == 5:
+            l = int(rng.integers(0, total + 1)) if rng.integers(8) else total + int(rng.integers(1, 50))
+            if l > total: expect_err(lambda: dec.set_offset_limit(l), lambda e: e.is_offset_out_of_range())
+            else: dec.set_offset_limit(l); lim = l
+        elif k == 6:
+            i = int(rng.integers(0, nf + 2))
+            if i >= nf: expect_err(lambda: dec.set_lower_frame(i), lambda e: e.is_frame_index_too_large())
+            else: assert dec.set_lower_frame(i) == fstart(i); off = fstart(i)
+        elif k == 7:
+            i = int(rng.integers(0, nf + 2))
+            if i >= nf: expect_err(lambda: dec.set_upper_frame(i), lambda e: e.is_frame_index_too_large())
+            else: assert dec.set_upper_frame(i) == fstart(i + 1); lim = fstart(i + 1)
+        elif k == 8:
+            w = int(rng.integers(3))
+            if w == 0: p = int(rng.integers(0, total + 20)); tgt = p
+            elif w == 1: p = int(rng.integers(-off - 5, total - off + 20)); tgt = off + p
+            else: p = int(rng.integers(-total - 5, 3)); tgt = total + p
+            bad = tgt < 0 or tgt > total or (w == 2 and p > 0)
+            if bad: expect_err(lambda: dec.seek(p, w), lambda e: e.is_offset_out_of_range())
+            else: assert dec.seek(p, w) == tgt; off = tgt
+        else:
+            dec.reset(); off, lim = 0, total
+            assert dec.read_compressed() == 0
+        assert dec.offset() == off and dec.offset_limit() == lim
+
+
+def check_encoder_random_ops(ctx, ops: int = 60, seed: int = 4, frame_size: int = 700, prefix: bool = False):
+    """differential test of Encoder framing against the contract of encode.rs:311-354, 438-472, 528-544, 626-775 as a model: a frame
+    holds at most frame_size input bytes; a frame that filled up is closed lazily by the next compress / end_frame / finish;
+    end_frame and finish always close a frame, an empty one included.  The archive must be one libzstd restores."""
+    import io
+    rng = np.random.default_rng(seed)
+    sink = io.BytesIO()
+    pfx = corpus.as_numpy(corpus.make_class("text", 3000, seed=seed + 1)) if prefix else None
+    enc = zk.EncodeOptions(ctx).frame_size_policy(zk.FrameSizePolicy.Uncompressed(frame_size)).checksum_flag(bool(seed & 1)).compression_level(3).into_encoder(sink)
+    src = corpus.as_numpy(corpus.make_mix(ops * 400, seed=seed, mix=corpus.CLASS_MIX_MIXED, segment=2048)).tobytes()
+    if prefix:
+        src = pfx.tobytes()[500:1500] + src[1000:]
+    pos, cur, model = 0, 0, []
+    for _ in range(ops):
+        if rng.integers(6) == 0:
+            enc.end_frame(); model.append(cur); cur = 0
+            continue
+        ln = int(rng.choice([0, 1, 13, frame_size - 1, frame_size, frame_size + 1, 3 * frame_size + 5, int(rng.integers(1, 2000))]))
+        chunk = src[pos: pos + ln]
+        done = 0
+        while done < len(chunk):
+            k = enc.compress_with_prefix(chunk[done:], pfx) if prefix else enc.compress(chunk[done:])
+            assert k > 0
+            done += k
+        left = len(chunk)
+        while left:
+            if cur == frame_size:
+                model.append(cur); cur = 0
+            take = min(left, frame_size - cur); cur += take; left -= take
+        pos += len(chunk)
+    total_written = enc.finish()
+    model.append(cur)
+    arc = sink.getvalue()
+    assert total_written == len(arc)
+    st = zk.SeekTable.from_bytes(arc, lib=ctx.lib)
+    got = [st.frame_size_decomp(i) for i in range(st.num_frames())]
+    assert got == model, (got[:12], model[:12], len(got), len(model))
+    cs = [st.frame_size_comp(i) for i in range(st.num_frames())]
+    assert st.size_comp() + st.into_serializer().encoded_len() == len(arc)
+    from util import offsets
+    out, sizes = O.ref_decompress_frames(np.frombuffer(arc, dtype=np.uint8)[: st.size_comp()], offsets(cs), offsets(got), prefix=pfx)
+    assert list(sizes) == got and out.tobytes() == src[:pos]
+    return len(model)

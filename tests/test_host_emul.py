@@ -21,6 +21,10 @@ def test_seek_table(emul_lib):
     cases.check_seek_table(emul_lib)
 
 
+def test_seek_table_parser_fuzz(emul_lib):
+    cases.check_seek_table_fuzz(emul_lib)
+
+
 @pytest.mark.parametrize("kind,level,fs,ck", [("text", 1, 20_000, False), ("text", 3, 9_000, True), ("structured", 3, 30_000, True),
                                                ("lowent", 5, 30_000, False), ("random", 1, 8_000, True), ("runs", 3, 30_000, True),
                                                ("text", 19, 30_000, True)])
@@ -127,6 +131,15 @@ def test_decoder_options(ctx):
 
 def test_decoder_state_machine(ctx):
     cases.check_decoder_state_machine(ctx)
+
+
+def test_encoder_random_ops(ctx):
+    assert cases.check_encoder_random_ops(ctx) > 20
+    cases.check_encoder_random_ops(ctx, ops=30, seed=9, frame_size=333, prefix=True)
+
+
+def test_decoder_random_ops(ctx):
+    cases.check_decoder_random_ops(ctx)
 
 
 def test_libzstd_archive_through_decoder(ctx):
