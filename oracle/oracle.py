@@ -32,9 +32,13 @@ SEEKABLE_MAX_FRAME_SIZE = 0x40000000        # lib.rs:58
 
 def build(force: bool = False) -> None:
     """compile the checkers (gcc only; a few seconds)"""
-    need = force or not all(os.path.exists(os.path.join(_REF, f)) for f in ("libzk_ref.so", "libzk_oracle.so"))
-    if need:
-        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    pairs = (("libzk_ref.so", "libzstd_driver.c"), ("libzk_oracle.so", "zstd_oracle.c"))
+    missing = not all(os.path.exists(os.path.join(_REF, so)) for so, _ in pairs)
+    stale = not missing and any(os.path.getmtime(os.path.join(_HERE, c)) > os.path.getmtime(os.path.join(_REF, so)) for so, c in pairs)
+    if force or missing or stale:          # (a prebuilt pair that is merely older than a fresh checkout's sources still loads if make is absent)
+        r = subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), capture_output=True)
+        if r.returncode != 0 and (force or missing):
+            raise RuntimeError("oracle build failed:\n" + r.stderr.decode(errors="replace"))
 
 
 _ref = None

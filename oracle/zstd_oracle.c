@@ -459,8 +459,14 @@ static int64_t decode_one_frame(const uint8_t* src, size_t n, uint8_t* dst, size
         if (fsz == 2) fcs += 256;
         pos += fsz; have_fcs = fsz > 0;
         if (single) fc->window = fcs;
+        /* ZSTD_decompressStream with a default DCtx (what the reference's Decoder holds, decode.rs:130-133) refuses windows above
+         * (1 << ZSTD_WINDOWLOG_LIMIT_DEFAULT) + 1 = 2^27 + 1 once the header is decoded */
+        if (fc->window > (1ULL << 27) + 1) FFAIL(ZE_WINDOW_TOO_LARGE);
     }
     size_t out = 0;
+    /* Block_Maximum_Size = min(Window_Size, 128 KiB), RFC 8878 3.1.1.2.3; libzstd: "Block Size Exceeds Maximum" for the content
+     * of a block, "Decompressed Block Size Exceeds Maximum" for what it regenerates (ZSTD_decompressContinue) */
+    const size_t bmax = fc->window < (1u << 17) ? (size_t)fc->window : (1u << 17);
     for (;;) {
         if (pos + 3 > n) FFAIL(ZE_SRC_SIZE_WRONG);
         uint32_t bh = src[pos] | (src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16);
@@ -468,20 +474,21 @@ static int64_t decode_one_frame(const uint8_t* src, size_t n, uint8_t* dst, size
         int last = bh & 1, type = (bh >> 1) & 3; size_t bsz = bh >> 3;
         if (type == 3) FFAIL(ZE_CORRUPTION);
         if (type == 0) {
-            if (bsz > (1u << 17)) FFAIL(ZE_CORRUPTION);
+            if (bsz > bmax) FFAIL(ZE_CORRUPTION);
             if (pos + bsz > n) FFAIL(ZE_SRC_SIZE_WRONG);
             if (out + bsz > cap) FFAIL(ZE_DST_TOO_SMALL);
             memcpy(dst + out, src + pos, bsz); pos += bsz; out += bsz;
         } else if (type == 1) {
-            if (bsz > (1u << 17)) FFAIL(ZE_CORRUPTION);
+            if (bsz > bmax) FFAIL(ZE_CORRUPTION);
             if (pos + 1 > n) FFAIL(ZE_SRC_SIZE_WRONG);
             if (out + bsz > cap) FFAIL(ZE_DST_TOO_SMALL);
             memset(dst + out, src[pos], bsz); pos += 1; out += bsz;
         } else {
-            if (bsz > (1u << 17)) FFAIL(ZE_CORRUPTION);
+            if (bsz > bmax) FFAIL(ZE_CORRUPTION);
             if (pos + bsz > n) FFAIL(ZE_SRC_SIZE_WRONG);
             int64_t r = decode_compressed_block(fc, src + pos, bsz, dst, out, cap);
             if (r < 0) { rc = r; goto done; }
+            if ((size_t)r > bmax) FFAIL(ZE_CORRUPTION);
             pos += bsz; out += (size_t)r;
         }
         if (last) break;

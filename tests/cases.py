@@ -162,8 +162,11 @@ def crafted_frames():
     repeat_first = _frame([(2, bytes([0x20]) + b"abcd" + bytes([0x01, 0xC0]) + bytes([0x01, 0x01]))])
     # a valid raw block, THEN a treeless block: the count pass must also see the missing tree in later blocks
     treeless_later = _frame([(0, b"hello world"), (2, bytes([0x43, 0x40, 0x00, 0x01, 0x00]))])
+    # Window_Descriptor 0xAA = 2^31 * 1.25: a valid header field, but above what a default DCtx accepts when streaming
+    # (ZSTD_WINDOWLOG_LIMIT_DEFAULT = 27): frameParameter_windowTooLarge (found by tests/emul/fuzz_decode.py)
+    big_window = b"\x28\xb5\x2f\xfd\x00\xaa" + (len(b"hello") << 3 | 1).to_bytes(3, "little") + b"hello"
     return [("overflow", crafted_overflow_frame(), 120_000), ("treeless_first", treeless_first, 4), ("repeat_first", repeat_first, 8),
-            ("treeless_later", treeless_later, 15)]
+            ("treeless_later", treeless_later, 15), ("big_window", big_window, 5)]
 
 
 # --- hand-built VALID frames for the cells of the matrix libzstd's encoder does not reach on demand ------------------
@@ -264,6 +267,35 @@ def check_special_entries(ctx):
     COVERAGE["dict_id_rejected"] = COVERAGE.get("dict_id_rejected", 0) + 1
 
 
+def check_window_limit(ctx):
+    """Window_Descriptor 0x88 (2^27, the streaming default limit) is accepted, 0x89 (2^27 * 1.125) is not -- as libzstd"""
+    body = (len(b"hello") << 3 | 1).to_bytes(3, "little") + b"hello"
+    for wd, code in ((0x88, 0), (0x89, 16), (0xF8, 16)):
+        fr = b"\x28\xb5\x2f\xfd\x00" + bytes([wd]) + body
+        out, sizes = O.ref_decompress_frames(np.frombuffer(fr, dtype=np.uint8), [0, len(fr)], [0, 5])
+        assert sizes[0] == (5 if code == 0 else -code), (hex(wd), sizes)
+        got, st, rc = decode_frames(ctx, [fr], [5], verify=True)
+        assert rc == -code and (code or got[:5] == b"hello"), (hex(wd), rc)
+    # Block_Maximum_Size = min(Window_Size, 128 KiB): a 1 KiB window (descriptor 0x00) takes a 1024-byte block, not a 1025-byte one,
+    # whether the block is Raw, RLE (regenerated size) or Compressed (RLE literals, no sequences) -- corruption_detected as libzstd
+    for nbytes, code in ((1024, 0), (1025, 20)):
+        payload = bytes(range(256)) * 5
+        for kind, blk in (("raw", ((nbytes << 3) | 1).to_bytes(3, "little") + payload[:nbytes]),
+                          ("rle", ((nbytes << 3) | (1 << 1) | 1).to_bytes(3, "little") + b"z"),
+                          ("lit", ((4 << 3) | (2 << 1) | 1).to_bytes(3, "little") + ((nbytes << 4) | (1 << 2) | 1).to_bytes(2, "little") + b"z\x00")):
+            fr = b"\x28\xb5\x2f\xfd\x00\x00" + blk
+            out, sizes = O.ref_decompress_frames(np.frombuffer(fr, dtype=np.uint8), [0, len(fr)], [0, nbytes])
+            assert sizes[0] == (nbytes if code == 0 else -code), (kind, nbytes, sizes)
+            try:
+                assert len(O.oracle_decompress(fr, nbytes)) == nbytes and code == 0
+            except O.ZstdError as e:
+                assert e.code == code, (kind, nbytes, e.code)
+            got, st, rc = decode_frames(ctx, [fr], [nbytes], verify=True)
+            assert rc == -code, (kind, nbytes, rc)
+            if code == 0:
+                assert got[:nbytes] == (payload[:nbytes] if kind == "raw" else b"z" * nbytes)
+
+
 def check_crafted_frames_rejected(ctx):
     """hand-built invalid frames: libzstd and the restatement say corruption; the codec must say so too, must not touch memory
     outside its buffers (tests/emul/asan_check.py runs this under ASan), and must still decode a good frame in the SAME batch"""
@@ -276,7 +308,7 @@ def check_crafted_frames_rejected(ctx):
                 raise AssertionError(f"{name}: the oracle accepted a crafted frame")
             except O.ZstdError as e:
                 code = e.code
-                assert code == (30 if name.startswith("treeless") else 20), (name, code)     # libzstd: dictionary_corrupted for a missing tree
+                assert code == (30 if name.startswith("treeless") else 16 if name == "big_window" else 20), (name, code)   # 30: dictionary_corrupted for a missing tree
         out, st, rc = decode_frames(ctx, [good[0], fr, good[0]], [gds[0], claim, gds[0]], verify=True)
         assert rc == -code and list(st) == [0, -code, 0], (name, rc, list(st))
         assert out[:20_000] == x.tobytes() and out[20_000 + claim:] == x.tobytes()

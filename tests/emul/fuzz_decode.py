@@ -20,7 +20,8 @@ from util import decode_frames
 
 secs = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-lib = N.load(build_emul(sanitize=os.environ.get("ZK_FUZZ_SANITIZE", "1") == "1"))
+# ZK_FUZZ_LIB=product: the nvcc build on a real GPU (optionally under compute-sanitizer) instead of the emulation build
+lib = N.load() if os.environ.get("ZK_FUZZ_LIB") == "product" else N.load(build_emul(sanitize=os.environ.get("ZK_FUZZ_SANITIZE", "1") == "1"))
 ctxs = {"default": zk.Context(0, lib)}
 for name, env in (("exec_v2", "ZK_EXEC_V2"), ("seq_v1", "ZK_SEQ_V1")):
     os.environ[env] = "1"; ctxs[name] = zk.Context(0, lib); del os.environ[env]

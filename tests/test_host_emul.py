@@ -125,6 +125,10 @@ def test_checksum_flag(ctx):
     cases.check_checksum_flag(ctx)
 
 
+def test_window_limit(ctx):
+    cases.check_window_limit(ctx)
+
+
 def test_decoder_options(ctx):
     cases.check_decoder_options(ctx)
 

@@ -99,6 +99,7 @@ struct ZkBlock {                 // one zstd block of one seek-table entry
     uint64_t fcs;                // last block of a zstd frame: Frame_Content_Size if ZKB_HAS_FCS
     uint32_t hash_start;         // last block: start (rel. to entry output) and length of the zstd frame's content
     uint32_t hash_len;
+    uint32_t bmax;               // Block_Maximum_Size of the block's zstd frame: min(Window_Size, 128 KiB)   [scan kernel]
 };
 #define ZKB_FIRST 1u             // first block of a zstd frame: resets repeat offsets / entropy tables
 #define ZKB_LAST 2u              // Last_Block

@@ -23,7 +23,7 @@
 // =============================================================================================
 struct ZkBlkInfo {
     uint32_t src, size; uint8_t type, flags;
-    uint32_t lit_size, nseq; uint8_t lit_type, modes, lit_hdr; uint64_t fcs;
+    uint32_t lit_size, nseq, bmax; uint8_t lit_type, modes, lit_hdr; uint64_t fcs;
 };
 
 struct ZkLitHdr { uint32_t type, hdr, regen, comp, streams; };
@@ -86,7 +86,12 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
         uint32_t hsz = 5 + (single ? 0 : 1) + did_sz + fcs_sz;
         if (n - pos < hsz) return ZKZ_SRC_SIZE_WRONG;
         uint32_t q = pos + 5;
-        if (!single) { uint32_t wd = p[q++]; if (10 + (wd >> 3) > 31) return ZKZ_WINDOW_TOO_LARGE; }
+        unsigned long long window = 0;
+        if (!single) {
+            const uint32_t wd = p[q++], wlog = 10 + (wd >> 3);
+            if (wlog > 31) return ZKZ_WINDOW_TOO_LARGE;                  // ZSTD_WINDOWLOG_MAX, refused while the header is parsed
+            window = (1ull << wlog) + ((1ull << wlog) >> 3) * (wd & 7);
+        }
         uint32_t dict = 0;
         for (uint32_t i = 0; i < did_sz; i++) dict |= (uint32_t)p[q + i] << (8 * i);
         q += did_sz;
@@ -94,6 +99,13 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
         unsigned long long fcs = 0;
         for (uint32_t i = 0; i < fcs_sz; i++) fcs |= (unsigned long long)p[q + i] << (8 * i);
         if (fcs_sz == 2) fcs += 256;
+        // the reference decodes with a default DCtx (decode.rs:130-133): streaming decompression refuses windows above
+        // 2^ZSTD_WINDOWLOG_LIMIT_DEFAULT (+1), after the dictionary check -- a Single_Segment frame's window is its content size
+        if (single) window = fcs;
+        if (window > (1ull << 27) + 1) return ZKZ_WINDOW_TOO_LARGE;
+        // Block_Maximum_Size = min(Window_Size, 128 KiB) (RFC 8878 3.1.1.2.3): libzstd refuses a block whose content or
+        // regenerated size exceeds it (ZSTD_decompressContinue: "Block Size Exceeds Maximum", "Decompressed Block Size Exceeds Maximum")
+        const uint32_t bsmax = window < ZK_BLOCK_MAX ? (uint32_t)window : ZK_BLOCK_MAX;
         pos += hsz;
         bool first = true;
         for (;;) {
@@ -101,20 +113,20 @@ __device__ int zk_walk_entry(const uint8_t* p, uint32_t n, Emit& emit) {
             uint32_t bh = zk_ld_le24(p + pos);
             uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
             if (type == 3) return ZKZ_CORRUPTION;
-            if (bsize > ZK_BLOCK_MAX) return ZKZ_CORRUPTION;
+            if (bsize > bsmax) return ZKZ_CORRUPTION;
             uint32_t content = type == 1 ? 1u : bsize;
             if (n - pos - 3 < content) return ZKZ_SRC_SIZE_WRONG;
             ZkBlkInfo bi;
             bi.src = pos + 3; bi.size = bsize; bi.type = (uint8_t)type;
             bi.flags = (uint8_t)((first ? ZKB_FIRST : 0) | (last ? ZKB_LAST : 0) | ((last && csum) ? ZKB_HAS_CSUM : 0) |
                                  ((last && fcs_sz) ? ZKB_HAS_FCS : 0));
-            bi.fcs = fcs; bi.lit_size = 0; bi.nseq = 0; bi.lit_type = 0; bi.modes = 0; bi.lit_hdr = 0;
+            bi.fcs = fcs; bi.bmax = bsmax; bi.lit_size = 0; bi.nseq = 0; bi.lit_type = 0; bi.modes = 0; bi.lit_hdr = 0;
             if (type == 2) {
                 const uint8_t* b = p + pos + 3;
                 if (bsize < 2) return ZKZ_CORRUPTION;
                 ZkLitHdr lh;
                 if (!zk_parse_lit_hdr(b, bsize, lh)) return ZKZ_CORRUPTION;
-                if (lh.regen > ZK_BLOCK_MAX) return ZKZ_CORRUPTION;
+                if (lh.regen > bsmax) return ZKZ_CORRUPTION;
                 uint32_t lsec = zk_lit_section_size(lh);
                 if (lsec >= bsize) return ZKZ_CORRUPTION;          // at least the nseq byte must follow
                 uint32_t nseq;
@@ -173,7 +185,7 @@ struct ZkFillEmit {
         b.lit_kind = 0; b.lit_byte = 0; b.lit_base = lit; b.seq_base = seq; b.nseq = bi.nseq; b.lit_size = bi.lit_size;
         b.lit_src = 0; b.regen = bi.type == 2 ? 0 : bi.size; b.status = 0; b.lit_status = 0;
         b.rep_out[0] = ZK_SYM_MAKE(0, 0); b.rep_out[1] = ZK_SYM_MAKE(1, 0); b.rep_out[2] = ZK_SYM_MAKE(2, 0);
-        b.fcs = bi.fcs; b.hash_start = 0; b.hash_len = 0;
+        b.fcs = bi.fcs; b.hash_start = 0; b.hash_len = 0; b.bmax = bi.bmax;
         if (bi.flags & ZKB_FIRST) { huf_ref = ll_ref = of_ref = ml_ref = -1; }
         b.huf_ref = -1; b.ll_ref = -1; b.of_ref = -1; b.ml_ref = -1;
         if (bi.type == 2) {
@@ -389,7 +401,7 @@ __device__ int zk_decode_block_sequences(ZkSeqSlot& sl, const ZkSeqTabs& tb, con
         o_lit[i] = lit_end; o_out[i] = out_end; o_off[i] = off;
     }
     if (!st && br.bp != 0) st = ZKZ_CORRUPTION;
-    if (!st && out_end + (blk.lit_size - lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
+    if (!st && out_end + (blk.lit_size - lit_end) > blk.bmax) st = ZKZ_CORRUPTION;
     a.blocks[bidx].rep_out[0] = r0; a.blocks[bidx].rep_out[1] = r1; a.blocks[bidx].rep_out[2] = r2;
     a.blocks[bidx].regen = out_end + (blk.lit_size - lit_end);
     return st;
@@ -672,7 +684,7 @@ __global__ void __launch_bounds__(32) zk_seq2_kernel(ZkDecodeArgs a) {
         if (chain_lane && live) {
             int st = ch.st;
             if (!st && cur != sb_bit) st = ZKZ_CORRUPTION;                                // every bit of the stream is consumed, no more
-            if (!st && ch.out_end + (lit_size - ch.lit_end) > ZK_BLOCK_MAX) st = ZKZ_CORRUPTION;
+            if (!st && ch.out_end + (lit_size - ch.lit_end) > a.blocks[bidx].bmax) st = ZKZ_CORRUPTION;
             a.blocks[bidx].rep_out[0] = ch.r0; a.blocks[bidx].rep_out[1] = ch.r1; a.blocks[bidx].rep_out[2] = ch.r2;
             a.blocks[bidx].regen = ch.out_end + (lit_size - ch.lit_end);
             a.blocks[bidx].status = st ? -st : 0;
