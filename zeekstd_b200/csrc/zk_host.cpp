@@ -373,7 +373,8 @@ struct zk_encoder {
     uint64_t written_compressed = 0;
     std::vector<uint8_t> batch;            // complete + partial frames not yet compressed (Uncompressed policy)
     std::vector<uint8_t> stage;
-    size_t batch_frames = 64;
+    size_t batch_frames = 8192;            // a GPU call takes the buffered complete frames once there are this many ...
+    size_t batch_bytes = (size_t)128 << 20; // ... or this many bytes of them (64 frames of 2 MiB; thousands of small ones: one launch sequence serves them all)
     const uint8_t* prefix = nullptr; size_t prefix_len = 0;   // prefix of the frames in `batch` (compress_with_prefix)
 
     int32_t sink(const uint8_t* p, size_t n) {
@@ -460,7 +461,7 @@ extern "C" int32_t zk_encoder_compress_with_prefix(zk_encoder* e, const uint8_t*
     // last complete frame in the buffer unless more input follows it.
     size_t complete = e->batch.size() / fs;
     if (complete && e->batch.size() % fs == 0) complete--;
-    if (complete >= e->batch_frames) { int32_t rc = e->flush_batch(complete * fs, nullptr, false); if (rc) return rc; }
+    if (complete >= e->batch_frames || (complete && complete * (size_t)fs >= e->batch_bytes)) { int32_t rc = e->flush_batch(complete * fs, nullptr, false); if (rc) return rc; }
     if (consumed) *consumed = len;
     return 0;
 }
