@@ -1056,7 +1056,7 @@ def check_decoder_random_ops(ctx, ops: int = 250, seed: int = 3, n: int = 24_000
     for _ in range(ops):
         k = int(rng.integers(10))
         if k <= 3:                                            # decompress
-            ln = int(rng.choice([0, 1, 7, 100, 1699, 1700, 1701, 5000, total]))
+            ln = int(rng.choice([0, 1, 7, 100, frame_size - 1, frame_size, frame_size + 1, 3 * frame_size - 100, total]))
             buf = bytearray(ln)
             got = dec.decompress(buf)
             want = data[off: min(off + ln, lim)] if lim > off else b""
@@ -1101,7 +1101,7 @@ def check_encoder_random_ops(ctx, ops: int = 60, seed: int = 4, frame_size: int 
     sink = io.BytesIO()
     pfx = corpus.as_numpy(corpus.make_class("text", 3000, seed=seed + 1)) if prefix else None
     enc = zk.EncodeOptions(ctx).frame_size_policy(zk.FrameSizePolicy.Uncompressed(frame_size)).checksum_flag(bool(seed & 1)).compression_level(3).into_encoder(sink)
-    src = corpus.as_numpy(corpus.make_mix(ops * 400, seed=seed, mix=corpus.CLASS_MIX_MIXED, segment=2048)).tobytes()
+    src = corpus.as_numpy(corpus.make_mix(ops * max(400, frame_size // 2), seed=seed, mix=corpus.CLASS_MIX_MIXED, segment=2048)).tobytes()
     if prefix:
         src = pfx.tobytes()[500:1500] + src[1000:]
     pos, cur, model = 0, 0, []

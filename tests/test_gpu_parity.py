@@ -180,6 +180,20 @@ def _table_sizes(st):
     return [st.frame_size_comp(i) for i in range(n)], [st.frame_size_decomp(i) for i in range(n)]
 
 
+def test_window_limit(ctx):
+    """Window_Size above the streaming default and blocks above Block_Maximum_Size = min(Window_Size, 128 KiB) are refused as by libzstd"""
+    cases.check_window_limit(ctx)
+
+
+def test_host_state_machines_random_ops(ctx):
+    """randomised differential tests of Decoder (offsets / limits / frames / seeks / resets) and Encoder (framing, lazy close, manual
+    end_frame, prefix) against models of the reference's contracts, larger than the emulator can afford"""
+    cases.check_decoder_random_ops(ctx, ops=600, seed=31, n=3_000_000, frame_size=100_000)
+    cases.check_decoder_random_ops(ctx, ops=300, seed=32, n=60_000, frame_size=1_700)
+    assert cases.check_encoder_random_ops(ctx, ops=200, seed=33, frame_size=40_000) > 20
+    cases.check_encoder_random_ops(ctx, ops=80, seed=36, frame_size=777, prefix=True)
+
+
 def test_api_encode_side(ctx):
     cases.check_cycle_tiny_buffers(ctx)
     cases.check_cycle_tiny_buffers(ctx, zk.FrameSizePolicy.Uncompressed(777))
