@@ -306,6 +306,64 @@ class Rig:
         return ec / steps, ed / steps, clen
 
 
+def c4_host_leg(parallel, codec, xr, nb, frame, level, dev, rank, steps, sync, pin):
+    """e2e of the configs[3] workload at N > 1: the root's input, archive and output live in (pinned) HOST memory; every step copies the input
+    up, runs the sharded passes, and copies the archive / the output down (copies not overlapped with the exchange: the root's PCIe link carries
+    every byte).  All ranks first agree that the root got its host buffers, so that nobody waits in a collective the root never enters.
+    -> the e2e dict on the root, None elsewhere or when the leg could not run.  (Runs on CPU tensors over gloo too: tests/test_parallel_gloo.py.)"""
+    import torch
+    import torch.distributed as dist
+    gib = 2.0**30
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    h_x = h_arc = h_out = None
+    if rank == 0:
+        try:
+            h_x = torch.empty(nb, dtype=torch.uint8, pin_memory=pin); h_x.copy_(xr[:nb])
+            h_arc = torch.empty(codec.compress_bound(nb, frame), dtype=torch.uint8, pin_memory=pin)
+            h_out = torch.empty(nb, dtype=torch.uint8, pin_memory=pin)
+        except (RuntimeError, MemoryError) as e:
+            sys.stderr.write(f"bench: no host buffers for the configs[3] e2e leg ({e}); keeping the per-rank figure\n")
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        return None
+    tc_w = td_w = 0.0
+    clen_e = 0
+    for it in range(steps + 1):                                          # first pass untimed
+        sync(); dist.barrier()
+        t0 = time.perf_counter()
+        if rank == 0:
+            xr[:nb].copy_(h_x, non_blocking=True)
+        frames, cs, ds = parallel.sharded_compress(codec, xr, nb, frame, level, True, device=dev)
+        clen_e = int(np.sum(cs))
+        if rank == 0:
+            h_arc[:clen_e].copy_(frames[:clen_e], non_blocking=True)
+        sync(); dist.barrier()
+        t1 = time.perf_counter()
+        if rank == 0:
+            frames[:clen_e].copy_(h_arc[:clen_e], non_blocking=True)
+        back = parallel.sharded_decompress(codec, frames, cs, ds, True, device=dev, frame_size=frame)
+        if rank == 0:
+            h_out.copy_(back[:nb], non_blocking=True)
+        sync(); dist.barrier()
+        t2 = time.perf_counter()
+        if it:
+            tc_w += t1 - t0; td_w += t2 - t1
+        del frames, back
+    tw = torch.tensor([tc_w / steps, td_w / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    if not torch.equal(h_out, h_x):
+        sys.stderr.write("bench: configs[3] host round trip MISMATCH; the e2e leg is dropped\n")
+        return None
+    ec4, ed4 = float(tw[0]), float(tw[1])
+    return {"value": round(2 * (nb / gib) / (ec4 + ed4), 3), "unit": "GiB/s", "h2d_bytes_per_step": int(nb + clen_e), "d2h_bytes_per_step": int(clen_e + nb),
+            "compress_GiBps": round(nb / gib / ec4, 3), "decompress_GiBps": round(nb / gib / ed4, 3), "steps": steps,
+            "api": "pinned host buffers on the root <-> root GPU <-> parallel.sharded_compress / sharded_decompress (NCCL); wall clock, copies not overlapped "
+                   "with the exchange -- the root's PCIe link carries every byte, so this figure does not grow with N"}
+
+
 def roofline_block(rig, alg_bytes, n):
     lib, ctx = rig.lib, rig.ctx
     kms = (ctypes.c_float * 8)(); kcnt = (ctypes.c_uint32 * 8)()
@@ -449,56 +507,9 @@ def main_ours(args, rank, world, local, ncores):
         del frames, back
     torch.cuda.synchronize(); dist.barrier()
     clocks4 = sampler.result()
-    # ---- e2e of THIS workload: the root's input, archive and output live in pinned HOST memory; every step copies the input up, runs the
-    # sharded passes, and copies the archive / the output down (copies not overlapped with the exchange: the root's PCIe link carries every byte).
-    # All ranks agree first that the root got its pinned buffers; otherwise the per-rank configs[1] figure stays and says what it is.
-    e2e4 = None
-    ok = torch.zeros(1, dtype=torch.int32, device=dev)
-    h_x = h_arc = h_out = None
-    if rank == 0:
-        try:
-            h_x = torch.empty(nb, dtype=torch.uint8, pin_memory=True); h_x.copy_(xr[:nb])
-            h_arc = torch.empty(codec.compress_bound(nb, FRAME), dtype=torch.uint8, pin_memory=True)
-            h_out = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
-            ok += 1
-        except (RuntimeError, MemoryError) as e:
-            sys.stderr.write(f"bench: no pinned host buffers for the configs[3] e2e leg ({e}); keeping the per-rank figure\n")
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if int(ok.item()) == 1:
-        e_steps = max(1, min(2, K))
-        tc_w = td_w = 0.0
-        for it in range(e_steps + 1):                                    # first pass untimed
-            torch.cuda.synchronize(); dist.barrier()
-            t0 = time.perf_counter()
-            if rank == 0:
-                xr[:nb].copy_(h_x, non_blocking=True)
-            frames, cs, ds = parallel.sharded_compress(codec, xr, nb, FRAME, C4_LEVEL, True, device=dev)
-            clen_e = int(np.sum(cs))
-            if rank == 0:
-                h_arc[:clen_e].copy_(frames[:clen_e], non_blocking=True)
-            torch.cuda.synchronize(); dist.barrier()
-            t1 = time.perf_counter()
-            if rank == 0:
-                frames[:clen_e].copy_(h_arc[:clen_e], non_blocking=True)
-            back = parallel.sharded_decompress(codec, frames, cs, ds, True, device=dev, frame_size=FRAME)
-            if rank == 0:
-                h_out.copy_(back[:nb], non_blocking=True)
-            torch.cuda.synchronize(); dist.barrier()
-            t2 = time.perf_counter()
-            if it:
-                tc_w += t1 - t0; td_w += t2 - t1
-            del frames, back
-        tw = torch.tensor([tc_w / e_steps, td_w / e_steps], dtype=torch.float64, device=dev)
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            assert torch.equal(h_out, h_x), "configs[3] host round trip mismatch"
-            ec4, ed4 = float(tw[0]), float(tw[1])
-            e2e4 = {"value": round(2 * (nb / gib) / (ec4 + ed4), 3), "unit": "GiB/s", "h2d_bytes_per_step": int(nb + clen_e), "d2h_bytes_per_step": int(clen_e + nb),
-                    "compress_GiBps": round(nb / gib / ec4, 3), "decompress_GiBps": round(nb / gib / ed4, 3), "steps": e_steps,
-                    "api": "pinned host buffers on the root <-> root GPU <-> parallel.sharded_compress / sharded_decompress (NCCL); wall clock, copies not overlapped "
-                           "with the exchange -- the root's PCIe link carries every byte, so this figure does not grow with N",
-                    "per_rank_configs1": e2e}
-    del h_x, h_arc, h_out
+    e2e4 = c4_host_leg(parallel, codec, xr, nb, FRAME, C4_LEVEL, dev, rank, max(1, min(2, K)), torch.cuda.synchronize, True)
+    if e2e4 is not None:
+        e2e4["per_rank_configs1"] = e2e
     launches4 = ctx.kernel_launches - launches0
     t4 = torch.tensor([tcs / K, tds / K], dtype=torch.float64, device=dev)
     dist.all_reduce(t4, op=dist.ReduceOp.MAX)

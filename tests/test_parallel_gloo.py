@@ -76,3 +76,44 @@ def test_frame_ranges():
     assert frame_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
     assert frame_ranges(0, 2) == [(0, 0), (0, 0)]
     assert frame_ranges(8192, 8)[-1] == (7168, 8192)
+
+
+def _leg_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import zeekstd_b200 as zk
+    from zeekstd_b200 import _native, corpus, parallel
+    from zeekstd_b200.build import build_emul
+    lib = _native.load(build_emul()); _native.set_default_lib(lib)
+    codec = parallel.HostCodec(zk.Context(0, lib))
+    nb, frame = 52_345, 8_000
+    xr = None
+    if rank == 0:
+        xr = codec.empty(nb)
+        xr[:nb] = corpus.make_class("text", nb, 6); xr[nb:] = 0
+    leg = bench.c4_host_leg(parallel, codec, xr, nb, frame, 3, "cpu", rank, 1, lambda: None, False)
+    if rank == 0:
+        q.put(leg)
+    else:
+        assert leg is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_configs3_host_leg_world2():
+    """bench.py's N > 1 e2e leg (root-held host buffers <-> sharded passes) on CPU tensors over gloo: same code, tiny input"""
+    from zeekstd_b200.build import build_emul
+    build_emul()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 29500 + (os.getpid() + 777) % 2000
+    procs = [ctxm.Process(target=_leg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    leg = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert leg is not None and leg["value"] >= 0 and leg["h2d_bytes_per_step"] == leg["d2h_bytes_per_step"] > 52_345 and leg["steps"] == 1
