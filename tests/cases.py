@@ -519,21 +519,21 @@ def check_patch_cycle(ctx, policy=None):
         COVERAGE["prefix_frames"] = COVERAGE.get("prefix_frames", 0) + len(frames)
 
 
-def check_prefix_batches(ctx, n: int = 300_000, frame_size: int = 50_000):
+def check_prefix_batches(ctx, n: int = 300_000, frame_size: int = 50_000, levels=(3,)):
     """prefix mode of the batch codec on more than one frame and more than one block per frame: text whose vocabulary lives
     in the prefix; both implementations, both directions, several prefix lengths (shorter and longer than the encoder's window)"""
     text = np.frombuffer(golden_bytes("dickens_96k.txt"), dtype=np.uint8)
     data = np.concatenate([text[10_000:60_000]] * (n // 50_000 + 1))[:n].copy()
     data[::977] ^= 1                                                   # not an exact copy of the prefix
-    for plen in (1, 1000, 40_000, 98_304):
+    for plen, level in [(p, l) for l in levels for p in (1, 1000, 40_000, 98_304)]:
         prefix = text[:plen]
-        comp, cs, ds = ctx.compress_frames(data, frame_size, 3, True, prefix=prefix)
+        comp, cs, ds = ctx.compress_frames(data, frame_size, level, True, prefix=prefix)
         out, sizes = O.ref_decompress_frames(comp, offsets(cs), offsets(ds), prefix=prefix)          # libzstd restores ours
         assert sizes == [int(d) for d in ds] and out.tobytes() == data.tobytes(), plen
         back, st, rc = ctx.decompress_frames(np.concatenate([comp, np.zeros(64, np.uint8)]), offsets(cs), offsets(ds), True, prefix=prefix)
         assert rc == 0 and back.tobytes() == data.tobytes()
         if plen >= 40_000:
-            plain = ctx.compress_frames(data, frame_size, 3, True)[0]
+            plain = ctx.compress_frames(data, frame_size, level, True)[0]
             assert comp.size < plain.size, (plen, comp.size, plain.size)        # the prefix was found
         frames, rcs, rds = O.ref_compress_frames(data, frame_size, 3, True, prefix=prefix)             # ours restores libzstd's
         back, st, rc = ctx.decompress_frames(np.frombuffer(b"".join(frames) + b"\0" * 64, dtype=np.uint8), offsets(rcs), offsets(rds), True, prefix=prefix)

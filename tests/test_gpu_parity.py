@@ -55,11 +55,15 @@ def test_compress_roundtrip(ctx, kind, level, fs, ck):
 
 
 def test_compression_levels_are_tiers(ctx):
-    """EncodeOptions::compression_level (encode.rs:176): three tiers here -- 1, 2-3, >= 4 -- each at least as dense as the one below
-    on the reference's corpus"""
+    """EncodeOptions::compression_level (encode.rs:176): five tiers here -- 1, 2-3, 4-6, 7-9, >= 10 -- each denser than the one below on the
+    reference's corpus, every tier's frames restored by libzstd (incl. a ragged tail, a checksum and a prefix on the two table-heavy tiers)"""
     d = corpus.dickens()[: 8 << 20]
-    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (1, 3, 4)]
-    assert sizes[0] > sizes[1] > sizes[2], sizes
+    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (1, 3, 4, 7, 10)]
+    assert sizes[0] > sizes[1] > sizes[2] > sizes[3] > sizes[4], sizes
+    for lvl in (7, 9, 10, 19):
+        for kind in ("text", "structured", "lowent", "random", "runs"):
+            cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 300_001, seed=lvl).numpy(), 131_072, lvl, lvl % 2 == 1)
+    cases.check_prefix_batches(ctx, n=400_000, levels=(7, 10))
 
 
 def test_compress_edge_sizes(ctx):

@@ -125,6 +125,18 @@ def test_checksum_flag(ctx):
     cases.check_checksum_flag(ctx)
 
 
+def test_high_level_tiers(ctx):
+    """levels 7-9 and >= 10 (8192-entry double table / 16384-entry table, one warp per CTA): libzstd restores their frames, with and without a
+    prefix, and they are denser than the tier below"""
+    d = np.frombuffer(cases.golden_bytes("dickens_96k.txt"), dtype=np.uint8)
+    sizes = [ctx.compress_frames(d, 1 << 20, lvl, False)[0].size for lvl in (4, 7, 10)]
+    assert sizes[0] > sizes[1] >= sizes[2], sizes
+    for lvl in (7, 10, 19):
+        for kind in ("text", "structured", "lowent", "random", "runs"):
+            cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 70_001, seed=lvl).numpy(), 40_000, lvl, lvl % 2 == 1)
+    cases.check_prefix_batches(ctx, n=120_000, levels=(7, 10))
+
+
 def test_window_limit(ctx):
     cases.check_window_limit(ctx)
 
