@@ -55,15 +55,11 @@ def test_compress_roundtrip(ctx, kind, level, fs, ck):
 
 
 def test_compression_levels_are_tiers(ctx):
-    """EncodeOptions::compression_level (encode.rs:176): five tiers here -- 1, 2-3, 4-6, 7-9, >= 10 -- each denser than the one below on the
-    reference's corpus, every tier's frames restored by libzstd (incl. a ragged tail, a checksum and a prefix on the two table-heavy tiers)"""
+    """EncodeOptions::compression_level (encode.rs:176): tiers 1, 2-3, 4-6 -- each denser than the one below on the reference's corpus
+    (tiers 7-9 and >= 10: test_zy_high_level_tiers)"""
     d = corpus.dickens()[: 8 << 20]
-    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (1, 3, 4, 7, 10)]
-    assert sizes[0] > sizes[1] > sizes[2] > sizes[3] > sizes[4], sizes
-    for lvl in (7, 9, 10, 19):
-        for kind in ("text", "structured", "lowent", "random", "runs"):
-            cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 300_001, seed=lvl).numpy(), 131_072, lvl, lvl % 2 == 1)
-    cases.check_prefix_batches(ctx, n=400_000, levels=(7, 10))
+    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (1, 3, 4)]
+    assert sizes[0] > sizes[1] > sizes[2], sizes
 
 
 def test_compress_edge_sizes(ctx):
@@ -300,6 +296,19 @@ def test_batched_range_reads(ctx):
     outs, nfr = seek.read_ranges(ctx, arch, np.array(st.c), np.array(st.d), offs, 70_000, max_batch_bytes=3 << 20)
     for o, got in zip(offs, outs):
         assert got == x[int(o): int(o) + 70_000].tobytes()
+
+
+def test_zy_high_level_tiers(ctx):
+    """levels 7-9 (8192-entry double table) and >= 10 (16384-entry table), one warp per CTA: denser than the tier below on the reference's
+    corpus, every frame restored by libzstd (ragged tail, checksum, prefix).  Added after the round's last GPU minutes: first run on a GPU is
+    the driver's, which is why it sits at the end of the file."""
+    d = corpus.dickens()[: 8 << 20]
+    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (4, 7, 10)]
+    assert sizes[0] > sizes[1] > sizes[2], sizes
+    for lvl in (7, 9, 10, 19):
+        for kind in ("text", "structured", "lowent", "random", "runs"):
+            cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 300_001, seed=lvl).numpy(), 131_072, lvl, lvl % 2 == 1)
+    cases.check_prefix_batches(ctx, n=400_000, levels=(7, 10))
 
 
 def test_zz_decoder_coverage_matrix(ctx):
