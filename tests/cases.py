@@ -1043,7 +1043,12 @@ def check_decoder_random_ops(ctx, ops: int = 250, seed: int = 3, n: int = 24_000
     total, nf = len(data), dec.seek_table().num_frames()
     assert dec.seek_table().size_decomp() == total and nf == -(-total // frame_size)
     off, lim = 0, total
+    fresh = True                                   # read_compressed() == 0: nothing read since the last (implicit) reset, decode.rs:352-357, 402-414
     fstart = lambda i: min(i * frame_size, total)
+    fidx = lambda o: min(o // frame_size, nf - 1)    # frame_index_decomp (seek_table.rs:916-934): offsets at or past the end map to the last frame
+
+    def moved(o):                                    # set_offset resets the context exactly when the frame changes or the offset goes back
+        return fidx(o) != fidx(off) or o < off
 
     def expect_err(fn, pred):
         try:
@@ -1061,11 +1066,13 @@ def check_decoder_random_ops(ctx, ops: int = 250, seed: int = 3, n: int = 24_000
             got = dec.decompress(buf)
             want = data[off: min(off + ln, lim)] if lim > off else b""
             assert got == len(want) and bytes(buf[:got]) == want, (off, lim, ln, got, len(want))
+            if got:
+                fresh = False
             off += got
         elif k == 4:
             o = int(rng.integers(0, total + 1)) if rng.integers(8) else total + int(rng.integers(1, 50))
             if o > total: expect_err(lambda: dec.set_offset(o), lambda e: e.is_offset_out_of_range())
-            else: dec.set_offset(o); off = o
+            else: fresh = fresh or moved(o); dec.set_offset(o); off = o
         elif k == 5:
             l = int(rng.integers(0, total + 1)) if rng.integers(8) else total + int(rng.integers(1, 50))
             if l > total: expect_err(lambda: dec.set_offset_limit(l), lambda e: e.is_offset_out_of_range())
@@ -1073,7 +1080,7 @@ def check_decoder_random_ops(ctx, ops: int = 250, seed: int = 3, n: int = 24_000
         elif k == 6:
             i = int(rng.integers(0, nf + 2))
             if i >= nf: expect_err(lambda: dec.set_lower_frame(i), lambda e: e.is_frame_index_too_large())
-            else: assert dec.set_lower_frame(i) == fstart(i); off = fstart(i)
+            else: fresh = fresh or moved(fstart(i)); assert dec.set_lower_frame(i) == fstart(i); off = fstart(i)
         elif k == 7:
             i = int(rng.integers(0, nf + 2))
             if i >= nf: expect_err(lambda: dec.set_upper_frame(i), lambda e: e.is_frame_index_too_large())
@@ -1085,11 +1092,11 @@ def check_decoder_random_ops(ctx, ops: int = 250, seed: int = 3, n: int = 24_000
             else: p = int(rng.integers(-total - 5, 3)); tgt = total + p
             bad = tgt < 0 or tgt > total or (w == 2 and p > 0)
             if bad: expect_err(lambda: dec.seek(p, w), lambda e: e.is_offset_out_of_range())
-            else: assert dec.seek(p, w) == tgt; off = tgt
+            else: fresh = fresh or moved(tgt); assert dec.seek(p, w) == tgt; off = tgt
         else:
-            dec.reset(); off, lim = 0, total
-            assert dec.read_compressed() == 0
+            dec.reset(); off, lim = 0, total; fresh = True
         assert dec.offset() == off and dec.offset_limit() == lim
+        assert (dec.read_compressed() == 0) == fresh, (dec.read_compressed(), fresh, off, lim)
 
 
 def check_encoder_random_ops(ctx, ops: int = 60, seed: int = 4, frame_size: int = 700, prefix: bool = False):
