@@ -1142,3 +1142,19 @@ def check_encoder_random_ops(ctx, ops: int = 60, seed: int = 4, frame_size: int 
     out, sizes = O.ref_decompress_frames(np.frombuffer(arc, dtype=np.uint8)[: st.size_comp()], offsets(cs), offsets(got), prefix=pfx)
     assert list(sizes) == got and out.tobytes() == src[:pos]
     return len(model)
+
+
+def check_encoder_golden(ctx):
+    """The encoder's bytes are deterministic (ties between lanes are resolved as sequential insertion would) and the SAME on every
+    build of the sources: tests/golden/encoder_golden.json was written from the CPU emulation build (any warp-scheduling seed gives these hashes);
+    the nvcc build on a GPU must reproduce it byte for byte -- which is also what lets ratios measured on one build be quoted for the other."""
+    import hashlib
+    import json
+    gold = json.loads(golden_bytes("encoder_golden.json"))
+    d = np.frombuffer(golden_bytes("dickens_96k.txt"), dtype=np.uint8)
+    for key, want in gold.items():
+        if key == "3+prefix":
+            comp, cs, ds = ctx.compress_frames(d[20_000:], 40_000, 3, True, prefix=d[:30_000])
+        else:
+            comp, cs, ds = ctx.compress_frames(d, 40_000, int(key), True)
+        assert int(comp.size) == want["size"] and hashlib.sha256(comp.tobytes()).hexdigest() == want["sha256"], (key, int(comp.size), want["size"])

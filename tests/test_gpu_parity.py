@@ -317,3 +317,10 @@ def test_zz_decoder_coverage_matrix(ctx):
     frames per entry, frames > 2 MiB, offsets > 1 MiB)"""
     totals = cases.check_coverage_matrix()
     print("coverage matrix:", totals)
+
+
+def test_zzz_encoder_bytes_are_pinned(ctx):
+    """the nvcc build reproduces, byte for byte, the compressed output the CPU emulation build of the same sources wrote into
+    tests/golden/encoder_golden.json (five level tiers + prefix mode) -- after the coverage-matrix test on purpose: written after the round's
+    last GPU minutes"""
+    cases.check_encoder_golden(ctx)

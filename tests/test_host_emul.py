@@ -125,6 +125,10 @@ def test_checksum_flag(ctx):
     cases.check_checksum_flag(ctx)
 
 
+def test_encoder_bytes_are_pinned(ctx):
+    cases.check_encoder_golden(ctx)
+
+
 def test_high_level_tiers(ctx):
     """levels 7-9 and >= 10 (8192-entry double table / 16384-entry table, one warp per CTA): libzstd restores their frames, with and without a
     prefix, and they are denser than the tier below"""
