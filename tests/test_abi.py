@@ -59,3 +59,27 @@ def test_product_never_links_the_oracle():
             if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
                 txt = open(os.path.join(d, f)).read()
                 assert "zko_" not in txt and "zkr_" not in txt and "dlopen" not in txt and "libzstd.so" not in txt, f
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/zeekstd_b200.h is what a foreign-language binding consumes: it must compile on its own as C99 and as C++11, and a C program
+    that touches every declared function must LINK against the product library (no compute: nothing is called)"""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "zeekstd_b200.h")
+    src = open(hdr).read()
+    names = sorted(set(re.findall(r"\b(zk_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", src, flags=re.S))))
+    names = [n for n in names if not n.endswith("_fn")]
+    c = tmp_path / "use.c"
+    c.write_text('#include "zeekstd_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void* f[] = {' + ", ".join(f"(const void*)&{n}" for n in names)
+                 + "};\n  printf(\"%u\\n\", (unsigned)(sizeof f / sizeof f[0]));\n  return 0;\n}\n")
+    inc = ["-I", os.path.join(root, "include")]
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only"] + inc + [str(c)], check=True, capture_output=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"] + inc + [str(c)], check=True, capture_output=True)
+    from zeekstd_b200 import _native
+    if os.path.exists(_native.PRODUCT_SO):
+        exe = tmp_path / "use"
+        r = subprocess.run(["gcc", "-std=c99"] + inc + [str(c), "-o", str(exe), _native.PRODUCT_SO, "-Wl,--unresolved-symbols=ignore-in-shared-libs"], capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+        assert len(names) > 60
