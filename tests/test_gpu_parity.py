@@ -298,6 +298,19 @@ def test_batched_range_reads(ctx):
         assert got == x[int(o): int(o) + 70_000].tobytes()
 
 
+def test_c_example_through_the_c_abi(tmp_path):
+    """examples/roundtrip.c compiled as C99 against include/zeekstd_b200.h and run against the product library: no Python between the caller
+    and the C ABI"""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi import _build_c_example
+    from zeekstd_b200 import _native
+    exe = _build_c_example(tmp_path, _native.PRODUCT_SO)
+    r = subprocess.run([str(exe)], capture_output=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith(b"ok: 100000 bytes"), (r.stdout, r.stderr)
+
+
 def test_zy_high_level_tiers(ctx):
     """levels 7-9 (8192-entry double table) and >= 10 (16384-entry table), one warp per CTA: denser than the tier below on the reference's
     corpus, every frame restored by libzstd (ragged tail, checksum, prefix).  Added after the round's last GPU minutes: first run on a GPU is
