@@ -103,3 +103,19 @@ def test_c_example_runs_on_the_emulation_build(tmp_path):
     exe = _build_c_example(tmp_path, build_emul())
     r = subprocess.run([str(exe)], capture_output=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith(b"ok: 100000 bytes"), (r.stdout, r.stderr)
+
+
+def test_rust_sys_binding_is_in_sync():
+    """bindings/rust/zeekstd_b200_sys.rs (generated by tools/gen_rust_sys.py; there is no rustc in this image to compile it) is up to date and
+    declares exactly the functions of the public header -- the same list the Python binding and the product library are held to"""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(root, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    text, names = gen.generate()
+    assert open(gen.OUT).read() == text, "run python tools/gen_rust_sys.py"
+    hdr = re.sub(r"/\*.*?\*/", "", open(gen.HDR).read(), flags=re.S)
+    declared = set(re.findall(r"\b(zk_[a-z0-9_]+)\s*\(", hdr)) - {"zk_write_fn", "zk_flush_fn"}
+    assert set(names) == declared and len(names) == len(set(names)), sorted(declared ^ set(names))
+    assert text.count("pub fn zk_") == len(names) and "*mut *mut zk_decoder" in text and "Option<unsafe extern \"C\" fn" in text
