@@ -73,6 +73,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def whole_direction(n_plain, n_comp, c_ms, d_ms, n_gpus):
+    """HBM roofline of each whole direction (not only the dominant kernel): algorithmic bytes = plain + compressed bytes of the job, over the
+    direction's device time, against n_gpus x the measured peak.  Pure arithmetic on numbers the line already carries."""
+    try:
+        peak, _ = peaks()
+        alg = float(n_plain + n_comp)
+        c, d = alg / (c_ms / 1e3) / 1e9, alg / (d_ms / 1e3) / 1e9
+        return {"algorithmic_bytes": int(alg), "compress_GBps": round(c, 1), "decompress_GBps": round(d, 1),
+                "compress_frac": round(c / (peak * n_gpus), 5), "decompress_frac": round(d / (peak * n_gpus), 5), "peak_GBps": peak * n_gpus}
+    except Exception:                                               # never worth losing the line for
+        return None
+
+
 class ClockSampler(threading.Thread):
     """samples SM clock / throttle reasons of one GPU during the timed region (NVML; nvidia-smi semantics)"""
 
@@ -452,7 +465,8 @@ def main_ours(args, rank, world, local, ncores):
                 "config": config_c1(n),
                 "statistic": "mean over the timed steps",
                 "compress_GiBps": round(n / gib / (tc_ms / 1e3), 3), "decompress_GiBps": round(n / gib / (td_ms / 1e3), 3),
-                "ratio": round(n / clen, 4), "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "config4_one_gpu": c4,
+                "ratio": round(n / clen, 4), "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
+                "roofline_whole_direction": whole_direction(n, clen, tc_ms, td_ms, 1), "config4_one_gpu": c4,
                 "cpu_baseline": cpu_baseline_block(x.cpu().numpy(), ncores, LEVEL, False, f"the {n >> 20} MiB workload")}
         print(json.dumps(line), flush=True)
         return 0
@@ -543,6 +557,8 @@ def main_ours(args, rank, world, local, ncores):
             "compress_GiBps": round(nb / gib / (c_ms / 1e3), 3), "decompress_GiBps": round(nb / gib / (d_ms / 1e3), 3), "ratio": round(nb / clen4, 4),
             "per_rank": per_rank, "limiting": limiting, "one_gpu_same_workload": one_gpu, "weak": weak,
             "gpu_launches": int(sum(float(a[-1]) for a in allr)), "clocks": clocks4, "e2e": e2e4 if e2e4 is not None else e2e, "roofline": roof,
+            "roofline_note": "`roofline` is the dominant kernel in rank 0's configs[1] pass (per-kernel events); `roofline_whole_direction` is THIS job",
+            "roofline_whole_direction": whole_direction(nb, clen4, c_ms, d_ms, world),
             "cpu_baseline": cpu_baseline_block(sample, ncores, C4_LEVEL, True, f"the first {sample.size >> 30} GiB of the workload")}
     print(json.dumps(line), flush=True)
     dist.destroy_process_group()
