@@ -312,16 +312,16 @@ def test_c_example_through_the_c_abi(tmp_path):
 
 
 def test_zy_high_level_tiers(ctx):
-    """levels 7-9 (8192-entry double table) and >= 10 (16384-entry table), one warp per CTA: denser than the tier below on the reference's
-    corpus, every frame restored by libzstd (ragged tail, checksum, prefix).  Added after the round's last GPU minutes: first run on a GPU is
+    """levels 7-9 (8192-entry double table), 10-12 (16384-entry table) and >= 13 (32768 entries over a 256 KiB history, dynamic shared memory),
+    one warp per CTA: denser than the tier below on the reference's corpus, every frame restored by libzstd (ragged tail, checksum, prefix).  Added after the round's last GPU minutes: first run on a GPU is
     the driver's, which is why it sits at the end of the file."""
     d = corpus.dickens()[: 8 << 20]
-    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (4, 7, 10)]
-    assert sizes[0] > sizes[1] > sizes[2], sizes
-    for lvl in (7, 9, 10, 19):
+    sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (4, 7, 10, 13)]
+    assert sizes[0] > sizes[1] > sizes[2] > sizes[3], sizes
+    for lvl in (7, 9, 10, 13, 19):
         for kind in ("text", "structured", "lowent", "random", "runs"):
             cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 300_001, seed=lvl).numpy(), 131_072, lvl, lvl % 2 == 1)
-    cases.check_prefix_batches(ctx, n=400_000, levels=(7, 10))
+    cases.check_prefix_batches(ctx, n=400_000, levels=(7, 10, 13))
 
 
 def test_zz_decoder_coverage_matrix(ctx):

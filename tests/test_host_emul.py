@@ -130,15 +130,19 @@ def test_encoder_bytes_are_pinned(ctx):
 
 
 def test_high_level_tiers(ctx):
-    """levels 7-9 and >= 10 (8192-entry double table / 16384-entry table, one warp per CTA): libzstd restores their frames, with and without a
-    prefix, and they are denser than the tier below"""
+    """levels 7-9, 10-12 and >= 13 (8192-entry double table / 16384-entry table / 32768-entry table over a 256 KiB history, one warp per CTA):
+    libzstd restores their frames, with and without a prefix, and each is denser than the tier below"""
     d = np.frombuffer(cases.golden_bytes("dickens_96k.txt"), dtype=np.uint8)
-    sizes = [ctx.compress_frames(d, 1 << 20, lvl, False)[0].size for lvl in (4, 7, 10)]
-    assert sizes[0] > sizes[1] >= sizes[2], sizes
-    for lvl in (7, 10, 19):
+    sizes = [ctx.compress_frames(d, 1 << 20, lvl, False)[0].size for lvl in (4, 7, 10, 13)]
+    assert sizes[0] > sizes[1] >= sizes[2] > sizes[3], sizes
+    comp, cs, ds = ctx.compress_frames(d, 1 << 20, 13, True)
+    assert comp[5] == 0x40 and cases.O.frame_stats(comp.tobytes())["zstd_frames"] == 1           # Window_Descriptor: 256 KiB
+    _, ss = cases.O.oracle_decompress_ex(comp.tobytes(), d.size)
+    assert ss["max_offset"] > 65_536                                                               # the wider window is used
+    for lvl in (7, 10, 13, 19):
         for kind in ("text", "structured", "lowent", "random", "runs"):
-            cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 40_001, seed=lvl).numpy(), 33_000, lvl, lvl % 2 == 1)
-    cases.check_prefix_batches(ctx, n=90_000, levels=(10,))
+            cases.check_compress_roundtrip(ctx, corpus.make_class(kind, 40_001 if lvl < 13 else 100_001, seed=lvl).numpy(), 33_000 if lvl < 13 else 100_001, lvl, lvl % 2 == 1)
+    cases.check_prefix_batches(ctx, n=90_000, levels=(10, 13))
 
 
 def test_window_limit(ctx):

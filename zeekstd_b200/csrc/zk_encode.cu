@@ -114,174 +114,35 @@ __global__ void __launch_bounds__(NW * 32) zk_match_kernel(ZkEncodeArgs a) {
     if (b >= a.n_blocks) return;
     uint16_t* table = tables[warp];
     uint16_t* tableL = table + (1 << HLOG);                // only touched when DFAST
-    size_t lo, hi, fstart;
-    zkc_block_range(a, b, lo, hi, fstart);
-    // history: up to one block of the same frame before `lo` is searchable (positions < 64 KiB fit the u16 table); the first
-    // block of a frame searches the tail of the prefix instead, through its staged copy
-    const bool pfx = a.ptail != 0 && lo == fstart;
-    const size_t base = lo - fstart >= ZKC_BLOCK ? lo - ZKC_BLOCK : fstart;
-    const uint8_t* sb = pfx ? a.pstage + (size_t)(b / a.blocks_per_frame) * ZKC_PSLOT : a.src + base;
-    const uint32_t lo32 = pfx ? a.ptail : (uint32_t)(lo - base), hi32 = lo32 + (uint32_t)(hi - lo);
-    for (int i = lane; i < ((DFAST ? 2 : 1) << HLOG); i += 32) table[i] = 0;
-    __syncwarp();
-    const uint32_t len = hi32 - lo32;
-    uint16_t* o_ll = a.seq_ll + (size_t)b * ZKC_MAXSEQ; uint16_t* o_ml = a.seq_ml + (size_t)b * ZKC_MAXSEQ;
-    uint32_t* o_off = a.seq_off + (size_t)b * ZKC_MAXSEQ;
-    uint8_t* o_lit = a.lits + (size_t)b * ZKC_BLOCK;
-    uint32_t nseq = 0, nlit = 0;
-    uint32_t ip = lo32;                                     // every literal byte below ip has been written to o_lit
-    if (len >= 16) {
-        const uint32_t mflimit = hi32 - 8;                  // last position where 8 bytes can be read
-        const uint32_t lt_mask = (1u << lane) - 1u;
-        const bool lazy = a.level >= 2;
-        // pre-insert the history so matches can reach into the previous block (or the prefix)
-        if (a.level >= 2 || pfx) {
-            for (uint32_t p0 = 0; p0 < lo32; p0 += 32) {
-                const uint32_t p = p0 + lane;
-                const unsigned long long v8 = p < lo32 ? zkc_ld8(sb + p) : 0ull;
-                const uint32_t hh = p < lo32 ? zkc_hash5<HLOG>(v8) : (0xFFFF0000u | (uint32_t)lane);
-                const uint32_t same = __match_any_sync(0xFFFFFFFFu, hh);
-                if (p < lo32 && lane == 31 - __clz((int)same)) table[hh] = (uint16_t)p;
-                if (DFAST) {
-                    const uint32_t hl = p < lo32 ? zkc_hash8<HLOG>(v8) : (0xFFFF0000u | (uint32_t)lane);
-                    const uint32_t sameL = __match_any_sync(0xFFFFFFFFu, hl);
-                    if (p < lo32 && lane == 31 - __clz((int)sameL)) tableL[hl] = (uint16_t)p;
-                }
-            }
-            __syncwarp();
-        }
-        uint32_t anchor = lo32;
-        uint32_t rep = 0;                                   // last emitted offset (0 = none)
-        // repeat-offset history (A.5) as the decoder will hold it: blocks are coded independently, so repeat codes are used
-        // only once three explicit offsets have been coded in this block (the history is then certain); the first block of a
-        // frame starts from the known {1,4,8}.  o_off receives Offset_Values (1..3 = repeat codes, offset + 3 otherwise).
-        uint32_t r0 = 1, r1 = 4, r2 = 8, known = lo == fstart ? 3u : 0u;
-        uint32_t misses = 0;                                // consecutive windows without a match: widen the stride (incompressible data)
-        uint32_t s_ll = 0, s_ml = 0, s_off = 0, flushed = 0; // staged sequences: slot nseq - flushed lives in that lane
-        for (;;) {
-            const uint32_t stride = 1u + min(misses >> 3, 3u);
-            if (ip + 32u * stride > mflimit) {
-                if (stride == 1) break;
-                misses = 0; continue;                       // the tail may still fit a stride-1 window
-            }
-            const uint32_t wb = ip;
-            const uint32_t p = wb + (uint32_t)lane * stride;
-            if (lane < 2) zk_prefetch_l1(sb + min(wb + 256u + 128u * (uint32_t)lane, hi32 - 1u));
-            const unsigned long long cur = zkc_ld8(sb + p);
-            const uint32_t h = zkc_hash5<HLOG>(cur);
-            const uint32_t cand = table[h];
-            uint32_t hl = 0, candL = 0;
-            if (DFAST) { hl = zkc_hash8<HLOG>(cur); candL = tableL[hl]; }
-            __syncwarp();
-            // several lanes may hash to the same slot: the highest position wins, as sequential insertion would leave it
-            // (keeps the compressed bytes deterministic)
-            const uint32_t same = __match_any_sync(0xFFFFFFFFu, h);
-            if (lane == 31 - __clz((int)same)) table[h] = (uint16_t)p;
-            if (DFAST) { const uint32_t sameL = __match_any_sync(0xFFFFFFFFu, hl); if (lane == 31 - __clz((int)sameL)) tableL[hl] = (uint16_t)p; }
-            // candidate from the hash table(s), and the repeat-offset candidate
-            uint32_t moff = 0, mlen0 = 0;
-            if (cand < p) {
-                const unsigned long long x = zkc_ld8(sb + cand) ^ cur;
-                const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
-                if (m >= ZKC_MINMATCH) { moff = p - cand; mlen0 = m; }
-            }
-            if (DFAST && candL < p && candL != cand) {
-                const unsigned long long x = zkc_ld8(sb + candL) ^ cur;
-                const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
-                if (m >= ZKC_MINMATCH && m > mlen0) { moff = p - candL; mlen0 = m; }       // both 8 long: the nearer one (5-byte table) is kept
-            }
-            if (rep && p >= rep) {
-                const unsigned long long x = zkc_ld8(sb + p - rep) ^ cur;
-                const uint32_t m = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
-                if (m >= 4 && m + 1 >= mlen0) { moff = rep; mlen0 = m; }
-            }
-            const uint32_t found = __ballot_sync(0xFFFFFFFFu, mlen0 != 0);
-            if (stride > 1) {
-                if (found) { misses = 0; continue; }        // compressible again: redo this window at stride 1
-                // the whole window is literals, straight from the registers
-                uint8_t* o = o_lit + nlit + (uint32_t)lane * stride;
-                o[0] = (uint8_t)cur; o[1] = (uint8_t)(cur >> 8);
-                if (stride > 2) o[2] = (uint8_t)(cur >> 16);
-                if (stride > 3) o[3] = (uint8_t)(cur >> 24);
-                nlit += 32u * stride; ip = wb + 32u * stride; misses++;
-                continue;
-            }
-            if (!found) {
-                o_lit[nlit + lane] = (uint8_t)cur;
-                nlit += 32u; ip = wb + 32u; misses++;
-                continue;
-            }
-            misses = 0;
-            // take every non-overlapping match of this window, left to right (one memory round trip serves them all)
-            const uint32_t packed = (moff << 4) | mlen0;
-            // a stride-1 window yields at most 8 sequences (matches are >= 4 bytes): make room in the 32 staging lanes first
-            if (nseq - flushed > 24u) {
-                if ((uint32_t)lane < nseq - flushed) { const uint32_t at = flushed + (uint32_t)lane; o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off; }
-                flushed = nseq;
-            }
-            uint32_t next_lane = 0;
-            bool cov = false;                               // this lane's byte is covered by a selected match
-            while (next_lane < 32) {
-                const uint32_t m = found & (0xFFFFFFFFu << next_lane);
-                if (!m) break;
-                int f = __ffs((int)m) - 1;
-                uint32_t mo = __shfl_sync(0xFFFFFFFFu, packed, f);          // (offset << 4) | length
-                // one step of lazy matching: a clearly longer match starting at the next position wins (one more literal)
-                if (lazy && (mo & 15u) < 8 && f < 31 && ((found >> (f + 1)) & 1u)) {
-                    const uint32_t mo2 = __shfl_sync(0xFFFFFFFFu, packed, f + 1);
-                    if ((mo2 & 15u) > (mo & 15u) + 1) { f++; mo = mo2; }
-                }
-                uint32_t ml = mo & 15u;
-                const uint32_t off = mo >> 4;
-                const uint32_t mpos = wb + (uint32_t)f;
-                if (ml == 8) {
-                    // extend cooperatively: lane k compares bytes [8 + 8k, 16 + 8k) of the match, 256 bytes a round
-                    for (;;) {
-                        const uint32_t q = mpos + ml + (uint32_t)lane * 8u;
-                        uint32_t eq = 8;
-                        if (q + 8 <= hi32) { const unsigned long long x = zkc_ld8(sb + q) ^ zkc_ld8(sb + q - off); if (x) eq = (uint32_t)(__ffsll((long long)x) - 1) >> 3; }
-                        else { eq = 0; for (uint32_t t = q; t < hi32 && sb[t] == sb[t - off]; t++) eq++; }
-                        const uint32_t stop = __ballot_sync(0xFFFFFFFFu, eq < 8);
-                        if (stop) { const int g = __ffs((int)stop) - 1; ml += 8 * g + __shfl_sync(0xFFFFFFFFu, eq, g); break; }
-                        ml += 256;
-                    }
-                }
-                // emit: literals [anchor, mpos) are already / will be placed by the windows that hold them
-                const uint32_t ll = mpos - anchor;
-                // after every sequence r0 == off; a repeat of r0 itself (ll != 0) leaves the history alone, every other
-                // case shifts (r0 -> r1) and drops r2, except the r1 hit, which swaps the first two
-                uint32_t ov = off + 3;
-                if (off != r0 && off != r1 && off != r2 && off + 1 != r0) {           // the common case: an explicit offset
-                    r2 = r1; r1 = r0; r0 = off; known += known < 3;
-                } else {
-                    bool hit0 = false, hit1 = false;
-                    if (known == 3) {
-                        const bool e0 = off == r0, e1 = off == r1, e2 = off == r2, em = r0 > 1 && off == r0 - 1;
-                        if (ll != 0) { if (e0) { ov = 1; hit0 = true; } else if (e1) { ov = 2; hit1 = true; } else if (e2) ov = 3; }
-                        else { if (e1) { ov = 1; hit1 = true; } else if (e2) ov = 2; else if (em) ov = 3; }
-                    } else known++;
-                    if (!hit0) { r2 = hit1 ? r2 : r1; r1 = r0; r0 = off; }
-                }
-                if (lane == (int)(nseq - flushed)) { s_ll = ll; s_ml = ml - 3; s_off = ov; }
-                nseq++;
-                cov = cov || (p - mpos < ml);               // unsigned: mpos <= p < mpos + ml
-                anchor = mpos + ml; rep = off;
-                next_lane = anchor - wb;                    // >= 32: the match runs past the window
-            }
-            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, !cov);
-            if (!cov) o_lit[nlit + __popc(lm & lt_mask)] = (uint8_t)cur;
-            nlit += (uint32_t)__popc(lm);
-            ip = anchor > wb + 32u ? anchor : wb + 32u;
-        }
-        if ((uint32_t)lane < nseq - flushed) {
-            const uint32_t at = flushed + (uint32_t)lane;
-            o_ll[at] = (uint16_t)s_ll; o_ml[at] = (uint16_t)s_ml; o_off[at] = s_off;
-        }
-    }
-    const uint32_t rest = hi32 - ip;
-    for (uint32_t i = lane; i < rest; i += 32) o_lit[nlit + i] = sb[ip + i];
-    nlit += rest;
-    if (lane == 0) { a.blocks[b].nseq = nseq; a.blocks[b].nlit = nlit; }
+#define ZKM_POS_T uint16_t
+#define ZKM_HIST_BYTES ZKC_BLOCK
+#include "zk_match_body.inc"
+#undef ZKM_POS_T
+#undef ZKM_HIST_BYTES
+}
+
+// Wide-history tier (level >= ZKC_WIDE_LEVEL): the same body with a history of ZKC_WIDE_HIST blocks of the frame instead of one -- the frame
+// header then announces a 256 KiB window (zk_frame_window_kernel) --, 32-bit positions, and one table of 2^HLOG entries in DYNAMIC shared memory
+// (128 KiB at HLOG 15: one warp-CTA per SM).  Every block still finds its matches alone and pre-inserts its whole history first, so a block costs
+// several times a level-3 block: a tier for ratio (2.50 on the reference's corpus against 2.40 in a 64 KiB window), not for speed.
+#define ZKC_WIDE_LEVEL 13
+#define ZKC_WIDE_HIST 7
+#define ZKC_WIDE_HLOG 15
+template <int HLOG>
+__global__ void __launch_bounds__(32) zk_match_wide_kernel(ZkEncodeArgs a) {
+    ZK_DYN_SMEM(wide_tab);
+    constexpr bool DFAST = false;
+    const int warp = 0, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x;
+    if (b >= a.n_blocks) return;
+    uint32_t* table = (uint32_t*)wide_tab;
+    uint32_t* tableL = table;                               // never touched (DFAST is false)
+    (void)warp; (void)tableL;
+#define ZKM_POS_T uint32_t
+#define ZKM_HIST_BYTES ((size_t)ZKC_WIDE_HIST * ZKC_BLOCK)
+#include "zk_match_body.inc"
+#undef ZKM_POS_T
+#undef ZKM_HIST_BYTES
 }
 
 // =============================================================================================
@@ -1081,6 +942,14 @@ __global__ void __launch_bounds__(1024) zk_frame_scan_kernel(ZkEncodeArgs a) {
     if (threadIdx.x == 0) { *a.total = carry; if (carry > a.dst_cap) *a.error = ZKZ_DST_TOO_SMALL; }
 }
 
+// wide-history tier only: the frame headers written by zk_frame_gather_kernel announce a 128 KiB window; offsets of this tier reach
+// (ZKC_WIDE_HIST + 1) blocks back, so the Window_Descriptor becomes 256 KiB (exponent 8, mantissa 0)
+__global__ void __launch_bounds__(128) zk_frame_window_kernel(ZkEncodeArgs a, uint32_t n_frames) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames || *a.error) return;
+    a.dst[a.frame_off[f] + 5] = 0x40;
+}
+
 // gather: one warp per block copies its staged bytes to the final position; block 0 of a frame also writes the
 // frame header, the last block the checksum
 __global__ void __launch_bounds__(128) zk_frame_gather_kernel(ZkEncodeArgs a) {
@@ -1221,15 +1090,20 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
         ZK_LAUNCH(zk_frame_hash_kernel, (n_frames + 3) / 4, 128, 0, ss, a);
     }
     ws->prof.begin(5, stream);
-    // five tiers (EncodeOptions::compression_level, encode.rs:176): 1 = 2048-entry table, no history, no lazy step; 2-3 = 4096 entries,
+    // six tiers (EncodeOptions::compression_level, encode.rs:176): 1 = 2048-entry table, no history, no lazy step; 2-3 = 4096 entries,
     // previous-block history, one lazy step; 4-6 = double table (8-byte + 5-byte hashes, 4096 entries each), two warps per CTA; 7-9 = double
-    // table of 8192 entries each, one warp per CTA; >= 10 = one table of 16384 entries (fewest collisions in a 64 KiB window), one warp per CTA.
-    // Ratio on the reference's corpus: 2.12 / 2.24 / 2.28 / 2.38 / 2.40 (profiles/ratio_dickens_r2.json)
+    // table of 8192 entries each, one warp per CTA; 10-12 = one table of 16384 entries, one warp per CTA; >= 13 = 256 KiB history, 32768 x u32
+    // entries in dynamic shared memory.  Ratio on the reference's corpus: 2.12 / 2.24 / 2.28 / 2.38 / 2.40 / 2.50 (profiles/ratio_dickens_r2.json)
     if (a.level <= 1) ZK_LAUNCH((zk_match_kernel<ZKC_HLOG_FAST, ZKC_C1_WARPS, false>), (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
     else if (a.level <= 3) ZK_LAUNCH((zk_match_kernel<ZKC_HLOG, ZKC_C1_WARPS, false>), (uint32_t)((n_blocks + ZKC_C1_WARPS - 1) / ZKC_C1_WARPS), ZKC_C1_WARPS * 32, 0, stream, a);
     else if (a.level <= 6) ZK_LAUNCH((zk_match_kernel<ZKC_HLOG, 2, true>), (uint32_t)((n_blocks + 1) / 2), 64, 0, stream, a);
     else if (a.level <= 9) ZK_LAUNCH((zk_match_kernel<13, 1, true>), (uint32_t)n_blocks, 32, 0, stream, a);
-    else ZK_LAUNCH((zk_match_kernel<14, 1, false>), (uint32_t)n_blocks, 32, 0, stream, a);
+    else if (a.level < ZKC_WIDE_LEVEL) ZK_LAUNCH((zk_match_kernel<14, 1, false>), (uint32_t)n_blocks, 32, 0, stream, a);
+    else {
+        const int wide_smem = (int)sizeof(uint32_t) << ZKC_WIDE_HLOG;
+        if (!ws->attr_set_wide) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_match_wide_kernel<ZKC_WIDE_HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem)); ws->attr_set_wide = true; }
+        ZK_LAUNCH((zk_match_wide_kernel<ZKC_WIDE_HLOG>), (uint32_t)n_blocks, 32, wide_smem, stream, a);
+    }
     ws->prof.end(5, stream);
     const size_t seq_smem = ((sizeof(ZkcTabs) + 15) & ~(size_t)15) + sizeof(ZkcSeqWarp) * ZKC_SW;
     if (!ws->attr_set) { ZKC_CUDA_OK(cudaFuncSetAttribute(zk_seq_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem)); ws->attr_set = true; }
@@ -1247,6 +1121,7 @@ int zk_encode_enqueue(ZkEncodeWs* ws, cudaStream_t stream, const uint8_t* d_src,
     ZK_LAUNCH(zk_frame_size_kernel, (n_frames + 255) / 256, 256, 0, stream, a);
     ZK_LAUNCH(zk_frame_scan_kernel, 1, 1024, 0, stream, a);
     ZK_LAUNCH(zk_frame_gather_kernel, (uint32_t)((n_blocks + 3) / 4), 128, 0, stream, a);
+    if (a.level >= ZKC_WIDE_LEVEL) { ZK_LAUNCH(zk_frame_window_kernel, (n_frames + 127) / 128, 128, 0, stream, a, n_frames); ws->launches++; }
     ws->prof.end(7, stream);
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes, a.frame_csize, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, stream));
     ZKC_CUDA_OK(cudaMemcpyAsync(ws->h_sizes + ws->cap_frames, a.total, 16, cudaMemcpyDeviceToHost, stream));
