@@ -27,7 +27,7 @@ while time.time() - t0 < secs:
     fs = int(rng.choice([1, 7, 100, 4096, 32767, 32768, 32769, 65536, 100_000, 1 << 20, 1 << 21, int(rng.integers(1, 300_000))]))
     if d.size // fs > 3000:
         fs = max(fs, d.size // 3000 + 1)
-    lvl = int(rng.choice([1, 2, 3, 4, 7, 19])); ck = bool(rng.integers(2))
+    lvl = int(rng.choice([1, 2, 3, 4, 7, 10, 13, 19])); ck = bool(rng.integers(2))
     pfx = None
     if rng.integers(4) == 0:
         pfx = corpus.make_class(kinds[rng.integers(3)], int(rng.integers(1, 100_000)), int(rng.integers(1 << 30))).numpy()
@@ -41,4 +41,4 @@ while time.time() - t0 < secs:
     back, st, rc = ctx.decompress_frames(comp, offsets(cs), offsets(ds), True, prefix=pfx)
     assert rc == 0 and np.array_equal(back[: d.size], d), ("own decode", rc, d.size, fs, lvl, ck)
     n_cases += 1; n_bytes += d.size
-print(f"encode fuzz clean: {n_cases} inputs, {n_bytes} bytes, levels 1/2/3/4/7/19, prefix on a quarter")
+print(f"encode fuzz clean: {n_cases} inputs, {n_bytes} bytes, levels 1/2/3/4/7/10/13/19, prefix on a quarter")
