@@ -56,7 +56,7 @@ def test_compress_roundtrip(ctx, kind, level, fs, ck):
 
 def test_compression_levels_are_tiers(ctx):
     """EncodeOptions::compression_level (encode.rs:176): tiers 1, 2-3, 4-6 -- each denser than the one below on the reference's corpus
-    (tiers 7-9 and >= 10: test_zy_high_level_tiers)"""
+    (tiers 7-9, 10-12 and >= 13: the last tests of this file)"""
     d = corpus.dickens()[: 8 << 20]
     sizes = [ctx.compress_frames(d, 2 << 20, lvl, False)[0].size for lvl in (1, 3, 4)]
     assert sizes[0] > sizes[1] > sizes[2], sizes
